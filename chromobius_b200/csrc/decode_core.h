@@ -1,0 +1,1412 @@
+// Per-shot decode path of the B200 decoder, written once for the device (nvcc, sm_100a) and for a
+// single-threaded host "simulation" build that tests/ uses to exercise the exact same logic without a GPU.
+//
+// Replaces, per shot (citations relative to /root/reference/src/chromobius):
+//   stage 1  lift-in            decode/decoder.cc:231-247   -> ingest_shot()
+//   stage 2  MWPM               decode/pymatcher.cc:27-42   -> match_shot()  (see "Matcher" below)
+//   stage 3  Euler tours        graph/euler_tours.h:89-112, graph/euler_tours.cc:21-97 -> lift_shot()
+//   stage 4  discharge          decode/decoder.cc:80-203, 268-276                     -> lift_shot()
+//
+// Matcher. The reference delegates stage 2 to PyMatching's sparse blossom. A B200 wants independent work items, so
+// the matcher here is a *certified local* exact MWPM:
+//   1. every event grows a Dijkstra ball on the Moebius CSR until it has seen its nearest event(s)   [parallel/event]
+//   2. events that saw each other are merged into components (lock-free union-find)                  [parallel/event]
+//   3. each component is solved exactly by a dense primal-dual blossom on the seen pair distances    [parallel/component]
+//   4. the blossom duals certify the component against every UNSEEN pair: y_a <= R_a/2 for all a implies
+//      y_a + y_b <= max(R_a, R_b) < d(a, b) for unseen (a, b), i.e. the duals stay feasible on the complete event graph,
+//      so the union of the component matchings is a global minimum-weight perfect matching. Events whose dual is too
+//      large for their ball (or that sit in an odd / unmatched component) re-grow their ball and the affected
+//      components are re-solved. Typical shots need 2-5 rounds and components of 2-6 events.
+//   5. matched pairs are expanded into graph edges along a canonical shortest path.
+// The total integer weight is exact (it is the optimum of the complete event graph); ties between equal-weight
+// matchings are broken by this file's own deterministic rules, not PyMatching's.
+//
+// Cooperative execution model: a *group* (1 thread, 1 warp or 1 block) decodes one shot. Loops over events /
+// components are strided by the group's thread id; `g.sync()` separates phases. The host build runs with a group of 1.
+#ifndef CHROMOBIUS_B200_DECODE_CORE_H
+#define CHROMOBIUS_B200_DECODE_CORE_H
+
+#include <cstddef>
+#include <cstdint>
+
+#include "tables.h"
+
+#ifdef __CUDACC__
+#define CB_HD __host__ __device__ __forceinline__
+#define CB_D __device__
+#else
+#define CB_HD inline
+#define CB_D inline
+#endif
+
+namespace cb200 {
+
+// Per-shot status codes (status_out). 0 = decoded.
+enum ShotStatus : uint32_t {
+    SHOT_OK = 0,
+    SHOT_SCRATCH_OVERFLOW = 1,      // retryable with larger scratch (the host does that, on the GPU)
+    SHOT_NO_PERFECT_MATCHING = 2,   // "No perfect matching exists for the detection events."
+    SHOT_EULER_FAILED = 3,          // "Graph didn't decompose into Euler tours."   (euler_tours.cc:81)
+    SHOT_DISCHARGE_FAILED = 4,      // "Failed to lift a flattened edge cycle ..."   (decoder.cc:176-202)
+    SHOT_ROUND_LIMIT = 5,
+    SHOT_COMPONENT_TOO_LARGE = 6,   // a matching component exceeded MAX_COMPONENT events
+};
+
+constexpr uint32_t MAX_COMPONENT = 250;  // endpoints are stored as u8 in the blossom's edge matrix
+constexpr uint32_t MAX_ROUNDS = 64;
+constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;
+
+struct NbEntry {
+    uint32_t ev;   // event index within the shot
+    uint32_t pad;
+    int64_t d;     // exact shortest-path distance
+};
+
+// Sizes of the scratch carved out of one group's arena.
+struct ScratchConfig {
+    uint32_t ht_log2;     // Dijkstra hash table slots per thread = 1 << ht_log2
+    uint32_t heap_cap;    // Dijkstra heap entries per thread
+    uint32_t found_cap;   // events one ball may report
+    uint32_t max_events;  // matcher events (2 x detection events) per shot the arena is sized for
+    uint64_t dyn_bytes;   // dynamic region (neighbour lists, blossom scratch, paths, Euler arrays)
+};
+
+// Launch-wide parameters.
+struct DecodeParams {
+    TablesView T;
+    const uint8_t *dets;         // [num_shots][stride] bit packed detection events
+    uint64_t stride;
+    uint32_t num_shots;
+    const uint32_t *shot_list;   // optional: indices of the shots to decode (retry passes); nullptr = 0..num_shots-1
+    uint32_t list_len;
+    uint64_t *obs_out;           // [num_shots]
+    int64_t *weight_out;         // [num_shots] (nullable)
+    uint32_t *status_out;        // [num_shots]
+    uint32_t *rounds_out;        // [num_shots] (nullable) matcher rounds, for statistics
+    // single-shot debug dump of the matched edges (nullable): interleaved node pairs, edge_dump_len = number of ints
+    int64_t *edge_dump;
+    uint64_t edge_dump_cap;
+    uint64_t *edge_dump_len;
+    // scratch
+    uint8_t *arena;              // num_groups * arena_stride bytes; persistent parts pre-initialised by init_arena
+    uint64_t arena_stride;
+    ScratchConfig cfg;
+    uint32_t *work_counter;      // persistent-kernel shot queue
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Atomics / group abstraction
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+CB_HD uint32_t cb_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { return atomicAdd((unsigned long long *)p, (unsigned long long)v); }
+CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
+CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+#else
+CB_HD uint32_t cb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { uint64_t o = *p; *p = o + v; return o; }
+CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { uint32_t o = *p; if (o == expect) *p = v; return o; }
+CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+#endif
+
+struct HostGroup {
+    int tid = 0;
+    int n = 1;
+    CB_HD void sync() const {}
+};
+
+CB_HD uint64_t align16(uint64_t x) { return (x + 15) & ~uint64_t{15}; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Arena layout of one group.
+//   [GroupHeader][per-thread Dijkstra scratch x n][node_slot: u32 x num_nodes][per-event arrays][dynamic region]
+// Persistent-clean invariants (established by init_group_arena, restored by every user):
+//   every Dijkstra hash key == HT_EMPTY, every node_slot == NO_INDEX.
+// ---------------------------------------------------------------------------------------------------------------
+struct GroupHeader {
+    uint32_t status;
+    uint32_t ncomp;
+    uint32_t mem_top;
+    uint32_t ngrow;
+    uint64_t dyn_top;     // bump pointer (bytes from dyn base)
+    uint64_t weight;      // total matched weight
+    uint32_t scan_tmp;
+    uint32_t pad[3];
+};
+
+struct DijkScratch {
+    uint32_t *key;    // [H]
+    int64_t *dist;    // [H]
+    uint32_t *used;   // [H] slots inserted (for O(touched) clean-up)
+    int64_t *hd;      // heap distances
+    uint32_t *hn;     // heap nodes
+    NbEntry *found;   // [found_cap]
+    uint32_t H, hcap, fcap;
+    uint32_t nused, hsize;
+};
+
+CB_HD uint64_t dijk_bytes(const ScratchConfig &c) {
+    uint64_t H = uint64_t{1} << c.ht_log2;
+    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(uint64_t{c.heap_cap} * 8) +
+           align16(uint64_t{c.heap_cap} * 4) + align16(uint64_t{c.found_cap} * sizeof(NbEntry));
+}
+
+// Per-event arrays (all sized max_events), see struct Shot.
+CB_HD uint64_t event_bytes(const ScratchConfig &c) {
+    uint64_t m = c.max_events;
+    // evdet(u32, m/2 -> m) R(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) uf root cnt start fillp members lidx
+    // comp_root path_off path_len (u32) dirty comp_dirty (u8) used_flag(u8)
+    return align16(m * 4) + align16(m * 8) + align16(m * 4) * 2 + align16(m * 4) + align16(m * 8) + align16(m * 4) +
+           align16(m * 4) * 9 + align16(m) * 3;
+}
+
+CB_HD uint64_t row_bytes(uint32_t num_dets) {
+    uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
+    return align16(nwords * 4) + align16((nwords + 1) * 4);
+}
+
+CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t group_threads) {
+    return align16(sizeof(GroupHeader)) + group_threads * dijk_bytes(c) + align16(uint64_t{num_nodes} * 4) +
+           row_bytes(num_nodes / 2) + event_bytes(c) + align16(c.dyn_bytes);
+}
+
+// Everything one group needs to decode one shot. Every thread of the group holds an identical copy (pointers are
+// computed with the same arithmetic), except `dj`, which is the thread's own Dijkstra scratch.
+struct Shot {
+    TablesView T;
+    ScratchConfig cfg;
+    GroupHeader *hdr;
+    DijkScratch dj;
+    uint32_t *node_slot;   // [num_nodes] persistent-clean
+    uint32_t *words;       // masked detection-event bits as little-endian u32 words
+    uint32_t *word_rank;   // [nwords + 1] exclusive prefix popcount
+    uint32_t nwords;
+    uint32_t M;            // matcher events = 2 * detection events
+    // per event
+    uint32_t *evdet;       // [M/2] ascending detector ids
+    int64_t *R;            // explored radius
+    uint32_t *nb_off, *nb_cnt;
+    uint32_t *grow_ev;
+    int64_t *grow_to;
+    int32_t *partner;
+    uint32_t *uf, *root, *cnt, *start, *fillp, *members, *lidx, *comp_root, *path_off, *path_len;
+    uint8_t *dirty, *comp_dirty, *used_flag;
+    // dynamic region
+    uint8_t *dyn;
+    uint64_t dyn_cap;
+
+    CB_HD uint32_t event_node(uint32_t i) const { return 2 * evdet[i >> 1] + (i & 1); }
+    CB_HD bool node_is_event(uint32_t node) const {
+        uint32_t d = node >> 1;
+        return (words[d >> 5] >> (d & 31)) & 1;
+    }
+    CB_HD uint32_t node_event_index(uint32_t node) const {
+        uint32_t d = node >> 1;
+        uint32_t w = words[d >> 5] & ((1u << (d & 31)) - 1);
+#ifdef __CUDA_ARCH__
+        uint32_t r = word_rank[d >> 5] + __popc(w);
+#else
+        uint32_t r = word_rank[d >> 5] + (uint32_t)__builtin_popcount(w);
+#endif
+        return 2 * r + (node & 1);
+    }
+    CB_HD void fail(uint32_t code) const { cb_atomic_max(&hdr->status, code); }
+    // Thread-safe bump allocation from the dynamic region; returns nullptr (and flags overflow) when exhausted.
+    CB_HD uint8_t *alloc(uint64_t bytes) const {
+        bytes = align16(bytes);
+        uint64_t off = cb_atomic_add64(&hdr->dyn_top, bytes);
+        if (off + bytes > dyn_cap) {
+            fail(SHOT_SCRATCH_OVERFLOW);
+            return nullptr;
+        }
+        return dyn + off;
+    }
+};
+
+template <class G>
+CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, const G &g) {
+    s.T = p.T;
+    s.cfg = p.cfg;
+    uint8_t *q = arena;
+    s.hdr = (GroupHeader *)q;
+    q += align16(sizeof(GroupHeader));
+    uint64_t H = uint64_t{1} << p.cfg.ht_log2;
+    uint8_t *mine = q + (uint64_t)g.tid * dijk_bytes(p.cfg);
+    s.dj.key = (uint32_t *)mine; mine += align16(H * 4);
+    s.dj.dist = (int64_t *)mine; mine += align16(H * 8);
+    s.dj.used = (uint32_t *)mine; mine += align16(H * 4);
+    s.dj.hd = (int64_t *)mine; mine += align16(uint64_t{p.cfg.heap_cap} * 8);
+    s.dj.hn = (uint32_t *)mine; mine += align16(uint64_t{p.cfg.heap_cap} * 4);
+    s.dj.found = (NbEntry *)mine;
+    s.dj.H = (uint32_t)H;
+    s.dj.hcap = p.cfg.heap_cap;
+    s.dj.fcap = p.cfg.found_cap;
+    s.dj.nused = 0;
+    s.dj.hsize = 0;
+    q += (uint64_t)g.n * dijk_bytes(p.cfg);
+    s.node_slot = (uint32_t *)q; q += align16(uint64_t{p.T.num_nodes} * 4);
+    s.nwords = (p.T.num_dets + 31) / 32;
+    s.words = (uint32_t *)q; q += align16(uint64_t{s.nwords} * 4);
+    s.word_rank = (uint32_t *)q; q += align16((uint64_t{s.nwords} + 1) * 4);
+    uint64_t m = p.cfg.max_events;
+    s.evdet = (uint32_t *)q; q += align16(m * 4);
+    s.R = (int64_t *)q; q += align16(m * 8);
+    s.nb_off = (uint32_t *)q; q += align16(m * 4);
+    s.nb_cnt = (uint32_t *)q; q += align16(m * 4);
+    s.grow_ev = (uint32_t *)q; q += align16(m * 4);
+    s.grow_to = (int64_t *)q; q += align16(m * 8);
+    s.partner = (int32_t *)q; q += align16(m * 4);
+    uint32_t **arrs[] = {&s.uf, &s.root, &s.cnt, &s.start, &s.fillp, &s.members, &s.lidx, &s.comp_root, &s.path_off};
+    for (auto a : arrs) { *a = (uint32_t *)q; q += align16(m * 4); }
+    s.path_len = s.fillp;  // fillp is dead once the matcher has finished; path_len is only used afterwards
+    s.dirty = q; q += align16(m);
+    s.comp_dirty = q; q += align16(m);
+    s.used_flag = q; q += align16(m);
+    s.dyn = q;
+    s.dyn_cap = align16(p.cfg.dyn_bytes);
+    s.M = 0;
+}
+
+// Called once per group before the first shot (and by the host after allocating a fresh arena).
+template <class G>
+CB_HD void init_group_arena(Shot &s, const G &g) {
+    for (uint32_t k = 0; k < s.dj.H; k++) s.dj.key[k] = HT_EMPTY;
+    for (uint32_t k = g.tid; k < s.T.num_nodes; k += g.n) s.node_slot[k] = NO_INDEX;
+    g.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 1: lift-in (decode/decoder.cc:231-247). The masked row doubles as the node -> event index map.
+// Returns through s.M. Pad bits and ignored detectors are cleared by the ingest mask.
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD uint32_t popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+CB_HD uint32_t ctz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
+template <class G>
+CB_HD void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
+    const uint32_t nb = s.T.num_det_bytes;
+    for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 4; b++) {
+            uint32_t k = 4 * w + b;
+            if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
+        }
+        s.words[w] = v;
+    }
+    if (g.tid == 0) {
+        s.hdr->status = 0;
+        s.hdr->dyn_top = 0;
+        s.hdr->weight = 0;
+    }
+    g.sync();
+    // exclusive prefix popcount: chunked, one serial pass over the per-thread sums
+    uint32_t chunk = (s.nwords + g.n - 1) / g.n;
+    uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
+    if (lo > s.nwords) lo = s.nwords;
+    if (hi > s.nwords) hi = s.nwords;
+    uint32_t sum = 0;
+    for (uint32_t w = lo; w < hi; w++) sum += popc32(s.words[w]);
+    // reuse `cnt` (per-event array, >= group size? not guaranteed) -> use uf scratch only if it fits; else serial
+    // Simple and robust: thread sums go to word_rank[lo] temporarily.
+    if (lo < hi) s.word_rank[lo] = sum;
+    g.sync();
+    if (g.tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t t = 0; t < (uint32_t)g.n; t++) {
+            uint32_t tlo = t * chunk;
+            if (tlo >= s.nwords) break;
+            uint32_t v = s.word_rank[tlo];
+            s.word_rank[tlo] = run;
+            run += v;
+        }
+        s.word_rank[s.nwords] = run;
+        s.hdr->scan_tmp = run;
+    }
+    g.sync();
+    uint32_t total = s.hdr->scan_tmp;
+    if (2 * total > s.cfg.max_events) {
+        if (g.tid == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        s.M = 0;
+        g.sync();
+        return;
+    }
+    if (lo < hi) {
+        uint32_t run = s.word_rank[lo];
+        for (uint32_t w = lo; w < hi; w++) {
+            s.word_rank[w] = run;
+            uint32_t v = s.words[w];
+            while (v) {
+                uint32_t b = ctz32(v);
+                v &= v - 1;
+                s.evdet[run++] = 32 * w + b;
+            }
+        }
+    }
+    s.M = 2 * total;
+    g.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Truncated Dijkstra on the Moebius CSR with a per-thread open-addressing table and a lazy binary heap.
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD uint32_t ht_hash(uint32_t node, uint32_t H) { return (node * 2654435761u) & (H - 1); }
+
+// Returns the slot of `node`, inserting it with dist = -1 when absent. Returns HT_EMPTY on table overflow.
+CB_HD uint32_t ht_slot(DijkScratch &dj, uint32_t node) {
+    uint32_t k = ht_hash(node ^ (node >> 7), dj.H);
+    while (true) {
+        uint32_t cur = dj.key[k];
+        if (cur == node) return k;
+        if (cur == HT_EMPTY) {
+            if (dj.nused * 4 >= dj.H * 3) return HT_EMPTY;
+            dj.key[k] = node;
+            dj.dist[k] = -1;
+            dj.used[dj.nused++] = k;
+            return k;
+        }
+        k = (k + 1) & (dj.H - 1);
+    }
+}
+CB_HD int64_t ht_get(const DijkScratch &dj, uint32_t node) {
+    uint32_t k = ht_hash(node ^ (node >> 7), dj.H);
+    while (true) {
+        uint32_t cur = dj.key[k];
+        if (cur == node) return dj.dist[k];
+        if (cur == HT_EMPTY) return -1;
+        k = (k + 1) & (dj.H - 1);
+    }
+}
+CB_HD void ht_clear(DijkScratch &dj) {
+    for (uint32_t k = 0; k < dj.nused; k++) dj.key[dj.used[k]] = HT_EMPTY;
+    dj.nused = 0;
+    dj.hsize = 0;
+}
+CB_HD bool heap_less(int64_t d1, uint32_t n1, int64_t d2, uint32_t n2) { return d1 < d2 || (d1 == d2 && n1 < n2); }
+CB_HD bool heap_push(DijkScratch &dj, int64_t d, uint32_t node) {
+    if (dj.hsize >= dj.hcap) return false;
+    uint32_t k = dj.hsize++;
+    while (k > 0) {
+        uint32_t p = (k - 1) >> 1;
+        if (!heap_less(d, node, dj.hd[p], dj.hn[p])) break;
+        dj.hd[k] = dj.hd[p];
+        dj.hn[k] = dj.hn[p];
+        k = p;
+    }
+    dj.hd[k] = d;
+    dj.hn[k] = node;
+    return true;
+}
+CB_HD void heap_pop(DijkScratch &dj, int64_t *d, uint32_t *node) {
+    *d = dj.hd[0];
+    *node = dj.hn[0];
+    uint32_t n = --dj.hsize;
+    if (n == 0) return;
+    int64_t ld = dj.hd[n];
+    uint32_t ln = dj.hn[n];
+    uint32_t k = 0;
+    while (true) {
+        uint32_t c = 2 * k + 1;
+        if (c >= n) break;
+        if (c + 1 < n && heap_less(dj.hd[c + 1], dj.hn[c + 1], dj.hd[c], dj.hn[c])) c++;
+        if (!heap_less(dj.hd[c], dj.hn[c], ld, ln)) break;
+        dj.hd[k] = dj.hd[c];
+        dj.hn[k] = dj.hn[c];
+        k = c;
+    }
+    dj.hd[k] = ld;
+    dj.hn[k] = ln;
+}
+
+// Grows the ball of event i.
+//   radius >= 0 : settle every node within `radius`, report every other event inside.
+//   radius <  0 : grow until more than `need_more_than` events have been seen, then finish that distance level.
+// Writes nb_off/nb_cnt/R of event i and marks i and every reported event dirty.
+CB_HD void explore_event(Shot &s, uint32_t i, int64_t radius, uint32_t need_more_than) {
+    DijkScratch &dj = s.dj;
+    const uint32_t src = s.event_node(i);
+    uint32_t nfound = 0;
+    int64_t limit = radius;
+    bool ok = true;
+    uint32_t k0 = ht_slot(dj, src);
+    dj.dist[k0] = 0;
+    heap_push(dj, 0, src);
+    while (dj.hsize) {
+        int64_t d;
+        uint32_t u;
+        heap_pop(dj, &d, &u);
+        if (limit >= 0 && d > limit) break;
+        if (d != ht_get(dj, u)) continue;
+        if (u != src && s.node_is_event(u)) {
+            if (nfound >= dj.fcap) { ok = false; break; }
+            dj.found[nfound].ev = s.node_event_index(u);
+            dj.found[nfound].pad = 0;
+            dj.found[nfound].d = d;
+            nfound++;
+            if (limit < 0 && nfound > need_more_than) limit = d;
+        }
+        const uint32_t e1 = s.T.row_ptr[u + 1];
+        for (uint32_t e = s.T.row_ptr[u]; e < e1; e++) {
+            AdjEntry a = s.T.adj[e];
+            int64_t nd = d + a.wt;
+            if (limit >= 0 && nd > limit) continue;
+            uint32_t k = ht_slot(dj, a.nbr);
+            if (k == HT_EMPTY) { ok = false; break; }
+            int64_t od = dj.dist[k];
+            if (od < 0 || nd < od) {
+                dj.dist[k] = nd;
+                if (!heap_push(dj, nd, a.nbr)) { ok = false; break; }
+            }
+        }
+        if (!ok) break;
+    }
+    ht_clear(dj);
+    if (!ok) {
+        s.fail(SHOT_SCRATCH_OVERFLOW);
+        return;
+    }
+    if (limit < 0) {
+        // Nothing more is reachable: this event cannot be paired (odd component of the Moebius graph).
+        s.fail(SHOT_NO_PERFECT_MATCHING);
+        return;
+    }
+    NbEntry *dst = (NbEntry *)s.alloc(uint64_t{nfound} * sizeof(NbEntry) + 16);
+    if (!dst) return;
+    for (uint32_t k = 0; k < nfound; k++) {
+        dst[k] = dj.found[k];
+        s.dirty[dj.found[k].ev] = 1;
+    }
+    s.dirty[i] = 1;
+    s.nb_off[i] = (uint32_t)(((uint8_t *)dst - s.dyn) >> 4);
+    s.nb_cnt[i] = nfound;
+    s.R[i] = limit;
+}
+CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry *)(s.dyn + ((uint64_t)s.nb_off[i] << 4)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense primal-dual blossom (maximum weight among maximum-cardinality matchings) over one component.
+// Vertices 1..n, blossoms n+1..NX-1. Edge (u, v) exists iff W[u][v] > 0. Doubled duals `lab` as in the classic
+// O(n^3) formulation: lab[u] + lab[v] >= 2 W(u, v), tight on matched edges.
+// All storage is caller provided (Shot::alloc); recursion is replaced by explicit stacks.
+// ---------------------------------------------------------------------------------------------------------------
+struct Blossom {
+    int n, n_x, NX, FL;
+    int64_t *W;        // (n+1) x (n+1)
+    uint8_t *ge;       // NX x NX x 2 : original endpoints (eu, ev) of the best edge between two nodes; eu == 0: none
+    int64_t *lab;      // NX
+    uint16_t *match, *slack, *st, *pa;
+    int8_t *S;
+    uint32_t *vis;
+    uint16_t *ff;      // flower_from: NX x (n+1)
+    uint16_t *fl;      // flower lists: (NX - n) x FL, row b - n
+    uint16_t *fl_len;  // NX
+    uint16_t *q;       // circular queue, capacity QC
+    uint16_t *stk;     // explicit stack, capacity 2*NX
+    int qh, qt, QC;
+    uint32_t vis_t;
+    bool broken;
+
+    static CB_HD uint64_t bytes_needed(int n) {
+        int NX = n + n / 2 + 2;
+        int FL = n + 2;
+        uint64_t b = 0;
+        b += align16(uint64_t(n + 1) * (n + 1) * 8);
+        b += align16(uint64_t(NX) * NX * 2);
+        b += align16(uint64_t(NX) * 8);
+        b += align16(uint64_t(NX) * 2) * 4;
+        b += align16(uint64_t(NX));
+        b += align16(uint64_t(NX) * 4);
+        b += align16(uint64_t(NX) * (n + 1) * 2);
+        b += align16(uint64_t(NX - n) * FL * 2);
+        b += align16(uint64_t(NX) * 2);
+        b += align16(uint64_t(2 * n + 4) * 2);
+        b += align16(uint64_t(2 * NX + 4) * 2);
+        return b;
+    }
+    CB_HD void bind(uint8_t *mem, int n_) {
+        n = n_;
+        NX = n + n / 2 + 2;
+        FL = n + 2;
+        QC = 2 * n + 4;
+        uint8_t *p = mem;
+        W = (int64_t *)p; p += align16(uint64_t(n + 1) * (n + 1) * 8);
+        ge = p; p += align16(uint64_t(NX) * NX * 2);
+        lab = (int64_t *)p; p += align16(uint64_t(NX) * 8);
+        match = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        slack = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        st = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        pa = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        S = (int8_t *)p; p += align16(uint64_t(NX));
+        vis = (uint32_t *)p; p += align16(uint64_t(NX) * 4);
+        ff = (uint16_t *)p; p += align16(uint64_t(NX) * (n + 1) * 2);
+        fl = (uint16_t *)p; p += align16(uint64_t(NX - n) * FL * 2);
+        fl_len = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        q = (uint16_t *)p; p += align16(uint64_t(QC) * 2);
+        stk = (uint16_t *)p;
+        broken = false;
+    }
+    CB_HD int64_t &w(int u, int v) { return W[u * (n + 1) + v]; }
+    CB_HD uint8_t &geu(int a, int b) { return ge[(a * NX + b) * 2]; }
+    CB_HD uint8_t &gev(int a, int b) { return ge[(a * NX + b) * 2 + 1]; }
+    CB_HD bool has(int a, int b) { return ge[(a * NX + b) * 2] != 0; }
+    CB_HD int64_t edist(int a, int b) {  // slack of the best edge between nodes a and b
+        int eu = geu(a, b), ev = gev(a, b);
+        return lab[eu] + lab[ev] - 2 * W[eu * (n + 1) + ev];
+    }
+    CB_HD uint16_t *flower(int b) { return fl + (b - n) * FL; }
+    CB_HD int flen(int b) { return b <= n ? 0 : fl_len[b]; }
+    CB_HD uint16_t &ffrom(int b, int x) { return ff[b * (n + 1) + x]; }
+
+    CB_HD void update_slack(int u, int x) {
+        if (!slack[x] || edist(u, x) < edist(slack[x], x)) slack[x] = (uint16_t)u;
+    }
+    CB_HD void set_slack(int x) {
+        slack[x] = 0;
+        for (int u = 1; u <= n; ++u)
+            if (has(u, x) && st[u] != x && S[st[u]] == 0) update_slack(u, x);
+    }
+    CB_HD void q_put(int v) {
+        q[qt] = (uint16_t)v;
+        qt = qt + 1 == QC ? 0 : qt + 1;
+        if (qt == qh) broken = true;
+    }
+    // depth-first, children in order
+    CB_HD void q_push(int x) {
+        int sp = 0;
+        stk[sp++] = (uint16_t)x;
+        while (sp) {
+            int y = stk[--sp];
+            if (y <= n) {
+                q_put(y);
+                continue;
+            }
+            uint16_t *f = flower(y);
+            for (int i = fl_len[y] - 1; i >= 0; --i) stk[sp++] = f[i];
+        }
+    }
+    CB_HD void set_st(int x, int b) {
+        int sp = 0;
+        stk[sp++] = (uint16_t)x;
+        while (sp) {
+            int y = stk[--sp];
+            st[y] = (uint16_t)b;
+            if (y <= n) continue;
+            uint16_t *f = flower(y);
+            for (int i = fl_len[y] - 1; i >= 0; --i) stk[sp++] = f[i];
+        }
+    }
+    CB_HD void reverse_tail(uint16_t *f, int len) {  // reverse f[1..len)
+        for (int a = 1, b = len - 1; a < b; ++a, --b) {
+            uint16_t t = f[a];
+            f[a] = f[b];
+            f[b] = t;
+        }
+    }
+    CB_HD int get_pr(int b, int xr) {
+        uint16_t *f = flower(b);
+        int len = fl_len[b];
+        int pr = 0;
+        while (pr < len && f[pr] != xr) pr++;
+        if (pr % 2 == 1) {
+            reverse_tail(f, len);
+            return len - pr;
+        }
+        return pr;
+    }
+    CB_HD void rotate_left(uint16_t *f, int len, int k) {  // three reversals
+        if (k <= 0 || k >= len) return;
+        for (int a = 0, b = k - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
+        for (int a = k, b = len - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
+        for (int a = 0, b = len - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
+    }
+    // set_match(u, v) with an explicit stack of (u, v) pairs.
+    CB_HD void set_match(int u0, int v0) {
+        int sp = 0;
+        stk[sp++] = (uint16_t)u0;
+        stk[sp++] = (uint16_t)v0;
+        while (sp) {
+            int v = stk[--sp];
+            int u = stk[--sp];
+            match[u] = gev(u, v);
+            if (u <= n) continue;
+            int eu = geu(u, v);
+            int xr = ffrom(u, eu);
+            int pr = get_pr(u, xr);
+            uint16_t *f = flower(u);
+            for (int i = 0; i < pr; ++i) {
+                stk[sp++] = f[i];
+                stk[sp++] = f[i ^ 1];
+            }
+            stk[sp++] = (uint16_t)xr;
+            stk[sp++] = (uint16_t)v;
+            rotate_left(f, fl_len[u], pr);
+        }
+    }
+    CB_HD void augment(int u, int v) {
+        for (;;) {
+            int xnv = st[match[u]];
+            set_match(u, v);
+            if (!xnv) return;
+            set_match(xnv, st[pa[xnv]]);
+            u = st[pa[xnv]];
+            v = xnv;
+        }
+    }
+    CB_HD int get_lca(int u, int v) {
+        for (++vis_t; u || v;) {
+            if (u != 0) {
+                if (vis[u] == vis_t) return u;
+                vis[u] = vis_t;
+                u = st[match[u]];
+                if (u) u = st[pa[u]];
+            }
+            int t = u; u = v; v = t;
+        }
+        return 0;
+    }
+    CB_HD void add_blossom(int u, int lca, int v) {
+        int b = n + 1;
+        while (b <= n_x && st[b]) ++b;
+        if (b > n_x) ++n_x;
+        if (b >= NX) { broken = true; return; }
+        lab[b] = 0;
+        S[b] = 0;
+        match[b] = match[lca];
+        uint16_t *f = flower(b);
+        int len = 0;
+        f[len++] = (uint16_t)lca;
+        for (int x = u, y; x != lca; x = st[pa[y]]) {
+            if (len + 2 > FL) { broken = true; return; }
+            f[len++] = (uint16_t)x;
+            f[len++] = (uint16_t)(y = st[match[x]]);
+            q_push(y);
+        }
+        reverse_tail(f, len);
+        for (int x = v, y; x != lca; x = st[pa[y]]) {
+            if (len + 2 > FL) { broken = true; return; }
+            f[len++] = (uint16_t)x;
+            f[len++] = (uint16_t)(y = st[match[x]]);
+            q_push(y);
+        }
+        fl_len[b] = (uint16_t)len;
+        set_st(b, b);
+        for (int x = 1; x <= n_x; ++x) geu(b, x) = geu(x, b) = 0;
+        for (int x = 1; x <= n; ++x) ffrom(b, x) = 0;
+        for (int i = 0; i < len; ++i) {
+            int xs = f[i];
+            for (int x = 1; x <= n_x; ++x)
+                if (has(xs, x) && (!has(b, x) || edist(xs, x) < edist(b, x))) {
+                    geu(b, x) = geu(xs, x);
+                    gev(b, x) = gev(xs, x);
+                    geu(x, b) = geu(x, xs);
+                    gev(x, b) = gev(x, xs);
+                }
+            for (int x = 1; x <= n; ++x)
+                if (ffrom(xs, x)) ffrom(b, x) = (uint16_t)xs;
+        }
+        set_slack(b);
+    }
+    CB_HD void expand_blossom(int b) {
+        uint16_t *f = flower(b);
+        int len = fl_len[b];
+        for (int i = 0; i < len; ++i) set_st(f[i], f[i]);
+        int xr = ffrom(b, geu(b, pa[b]));
+        int pr = get_pr(b, xr);
+        for (int i = 0; i < pr; i += 2) {
+            int xs = f[i], xns = f[i + 1];
+            pa[xs] = geu(xns, xs);
+            S[xs] = 1;
+            S[xns] = 0;
+            slack[xs] = 0;
+            set_slack(xns);
+            q_push(xns);
+        }
+        S[xr] = 1;
+        pa[xr] = pa[b];
+        for (int i = pr + 1; i < len; ++i) {
+            int xs = f[i];
+            S[xs] = -1;
+            set_slack(xs);
+        }
+        st[b] = 0;
+    }
+    // e = best edge between nodes a (row) and b: endpoints (eu in a, ev in b)
+    CB_HD bool on_found_edge(int eu, int ev) {
+        int u = st[eu], v = st[ev];
+        if (S[v] == -1) {
+            pa[v] = (uint16_t)eu;
+            S[v] = 1;
+            int nu = st[match[v]];
+            slack[v] = slack[nu] = 0;
+            S[nu] = 0;
+            q_push(nu);
+        } else if (S[v] == 0) {
+            int lca = get_lca(u, v);
+            if (!lca) {
+                augment(u, v);
+                augment(v, u);
+                return true;
+            }
+            add_blossom(u, lca, v);
+        }
+        return false;
+    }
+    CB_HD bool matching() {
+        const int64_t INF = INT64_MAX / 4;
+        for (int x = 1; x <= n_x; ++x) {
+            S[x] = -1;
+            slack[x] = 0;
+        }
+        qh = qt = 0;
+        for (int x = 1; x <= n_x; ++x)
+            if (st[x] == x && !match[x]) {
+                pa[x] = 0;
+                S[x] = 0;
+                q_push(x);
+            }
+        if (qh == qt) return false;
+        for (;;) {
+            while (qh != qt) {
+                if (broken) return false;
+                int u = q[qh];
+                qh = qh + 1 == QC ? 0 : qh + 1;
+                if (S[st[u]] == 1) continue;
+                for (int v = 1; v <= n; ++v)
+                    if (W[u * (n + 1) + v] > 0 && st[u] != st[v]) {
+                        if (lab[u] + lab[v] - 2 * W[u * (n + 1) + v] == 0) {
+                            if (on_found_edge(u, v)) return true;
+                        } else {
+                            update_slack(u, st[v]);
+                        }
+                    }
+            }
+            if (broken) return false;
+            int64_t d = INF;
+            for (int b = n + 1; b <= n_x; ++b)
+                if (st[b] == b && S[b] == 1) d = lab[b] / 2 < d ? lab[b] / 2 : d;
+            for (int x = 1; x <= n_x; ++x)
+                if (st[x] == x && slack[x]) {
+                    int64_t sd = edist(slack[x], x);
+                    if (S[x] == -1) d = sd < d ? sd : d;
+                    else if (S[x] == 0) d = sd / 2 < d ? sd / 2 : d;
+                }
+            if (d >= INF) return false;
+            for (int u = 1; u <= n; ++u) {
+                if (S[st[u]] == 0) lab[u] -= d;
+                else if (S[st[u]] == 1) lab[u] += d;
+            }
+            for (int b = n + 1; b <= n_x; ++b)
+                if (st[b] == b) {
+                    if (S[b] == 0) lab[b] += d * 2;
+                    else if (S[b] == 1) lab[b] -= d * 2;
+                }
+            qh = qt = 0;
+            for (int x = 1; x <= n_x; ++x)
+                if (st[x] == x && slack[x] && st[slack[x]] != x && edist(slack[x], x) == 0)
+                    if (on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+            for (int b = n + 1; b <= n_x; ++b)
+                if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(b);
+        }
+    }
+    // W must be filled (symmetric, 0 = absent). Returns the number of matched pairs; match[1..n] holds partners.
+    CB_HD int solve() {
+        n_x = n;
+        vis_t = 0;
+        for (int u = 0; u < NX; ++u) {
+            match[u] = 0;
+            st[u] = (uint16_t)(u <= n ? u : 0);
+            fl_len[u] = 0;
+            vis[u] = 0;
+            slack[u] = 0;
+            pa[u] = 0;
+            S[u] = -1;
+            lab[u] = 0;
+        }
+        int64_t w_max = 0;
+        for (int u = 1; u <= n; ++u)
+            for (int v = 1; v <= n; ++v) {
+                ffrom(u, v) = (uint16_t)(u == v ? u : 0);
+                int64_t x = W[u * (n + 1) + v];
+                if (x > 0) {
+                    geu(u, v) = (uint8_t)u;
+                    gev(u, v) = (uint8_t)v;
+                } else {
+                    geu(u, v) = 0;
+                    gev(u, v) = 0;
+                }
+                if (x > w_max) w_max = x;
+            }
+        for (int u = 1; u <= n; ++u) lab[u] = w_max;
+        int cnt = 0;
+        while (matching()) ++cnt;
+        return cnt;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 2 driver
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD uint32_t uf_find(uint32_t *uf, uint32_t x) {
+    while (true) {
+        uint32_t p = uf[x];
+        if (p == x) return x;
+        x = p;
+    }
+}
+CB_HD void uf_union(uint32_t *uf, uint32_t a, uint32_t b) {
+    while (true) {
+        a = uf_find(uf, a);
+        b = uf_find(uf, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        if (cb_atomic_cas(&uf[a], a, b) == a) return;  // hook the larger root under the smaller
+    }
+}
+
+// Exact distance between two events of the same component, taken from whichever ball saw the other.
+CB_HD int64_t seen_distance(const Shot &s, uint32_t i, uint32_t j) {
+    const NbEntry *l = nb_list(s, i);
+    for (uint32_t k = 0; k < s.nb_cnt[i]; k++)
+        if (l[k].ev == j) return l[k].d;
+    l = nb_list(s, j);
+    for (uint32_t k = 0; k < s.nb_cnt[j]; k++)
+        if (l[k].ev == i) return l[k].d;
+    return -1;
+}
+
+CB_HD void request_growth(Shot &s, uint32_t ev, int64_t to) {
+    uint32_t k = cb_atomic_add(&s.hdr->ngrow, 1);
+    s.grow_ev[k] = ev;
+    s.grow_to[k] = to;
+}
+
+// Solves component c (members sorted ascending). Either commits partners or requests growth.
+CB_HD void solve_component(Shot &s, uint32_t c) {
+    uint32_t r = s.comp_root[c];
+    uint32_t n = s.cnt[r];
+    uint32_t *mem = s.members + s.start[r];
+    // deterministic member order: insertion sort (components are small)
+    for (uint32_t a = 1; a < n; a++) {
+        uint32_t v = mem[a];
+        uint32_t b = a;
+        while (b > 0 && mem[b - 1] > v) {
+            mem[b] = mem[b - 1];
+            b--;
+        }
+        mem[b] = v;
+    }
+    if (n & 1) {
+        for (uint32_t a = 0; a < n; a++) request_growth(s, mem[a], -1);
+        return;
+    }
+    if (n == 2) {
+        // Closed form of the blossom on one edge: y = d/2 each, so both balls need radius >= d.
+        uint32_t i = mem[0], j = mem[1];
+        int64_t d = seen_distance(s, i, j);
+        bool ok = true;
+        if (d > s.R[i]) { request_growth(s, i, d); ok = false; }
+        if (d > s.R[j]) { request_growth(s, j, d); ok = false; }
+        if (ok) {
+            s.partner[i] = (int32_t)j;
+            s.partner[j] = (int32_t)i;
+        }
+        return;
+    }
+    if (n > MAX_COMPONENT) {
+        s.fail(SHOT_COMPONENT_TOO_LARGE);
+        return;
+    }
+    uint8_t *memory = s.alloc(Blossom::bytes_needed((int)n));
+    if (!memory) return;
+    Blossom bl;
+    bl.bind(memory, (int)n);
+    for (uint32_t a = 0; a < n; a++) s.lidx[mem[a]] = a + 1;
+    for (uint32_t k = 0; k < (n + 1) * (n + 1); k++) bl.W[k] = 0;
+    int64_t big = 2;
+    for (uint32_t a = 0; a < n; a++) {
+        const NbEntry *l = nb_list(s, mem[a]);
+        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++)
+            if (l[k].d + 2 > big) big = l[k].d + 2;
+    }
+    for (uint32_t a = 0; a < n; a++) {
+        const NbEntry *l = nb_list(s, mem[a]);
+        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++) {
+            uint32_t b = s.lidx[l[k].ev];
+            bl.w((int)a + 1, (int)b) = big - l[k].d;
+            bl.w((int)b, (int)a + 1) = big - l[k].d;
+        }
+    }
+    int pairs = bl.solve();
+    if (bl.broken) {
+        s.fail(SHOT_SCRATCH_OVERFLOW);
+        return;
+    }
+    if ((uint32_t)pairs * 2 != n) {
+        for (uint32_t a = 0; a < n; a++)
+            if (!bl.match[a + 1]) request_growth(s, mem[a], -1);
+        return;
+    }
+    bool ok = true;
+    for (uint32_t a = 0; a < n; a++) {
+        int64_t need = big - bl.lab[a + 1];  // = 2 * y_a
+        if (need > s.R[mem[a]]) {
+            request_growth(s, mem[a], need);
+            ok = false;
+        }
+    }
+    if (ok)
+        for (uint32_t a = 0; a < n; a++) s.partner[mem[a]] = (int32_t)mem[bl.match[a + 1] - 1];
+}
+
+template <class G>
+CB_HD uint32_t match_shot(Shot &s, const G &g) {
+    const uint32_t M = s.M;
+    for (uint32_t i = g.tid; i < M; i += g.n) {
+        s.partner[i] = -1;
+        s.dirty[i] = 0;
+        s.nb_cnt[i] = 0;
+        s.used_flag[i] = 0;
+    }
+    g.sync();
+    for (uint32_t i = g.tid; i < M; i += g.n) explore_event(s, i, -1, 0);
+    uint32_t round = 0;
+    while (true) {
+        g.sync();
+        if (s.hdr->status) return round;
+        if (++round > MAX_ROUNDS) {
+            if (g.tid == 0) s.fail(SHOT_ROUND_LIMIT);
+            g.sync();
+            return round;
+        }
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            s.uf[i] = i;
+            s.comp_dirty[i] = 0;
+            s.cnt[i] = 0;
+        }
+        if (g.tid == 0) {
+            s.hdr->ncomp = 0;
+            s.hdr->mem_top = 0;
+            s.hdr->ngrow = 0;
+        }
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            const NbEntry *l = nb_list(s, i);
+            for (uint32_t k = 0; k < s.nb_cnt[i]; k++) uf_union(s.uf, i, l[k].ev);
+        }
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            uint32_t r = uf_find(s.uf, i);
+            s.root[i] = r;
+            if (s.dirty[i]) s.comp_dirty[r] = 1;
+        }
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n)
+            if (s.comp_dirty[s.root[i]]) cb_atomic_add(&s.cnt[s.root[i]], 1);
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n)
+            if (s.root[i] == i && s.comp_dirty[i]) {
+                uint32_t slot = cb_atomic_add(&s.hdr->ncomp, 1);
+                s.comp_root[slot] = i;
+                s.start[i] = cb_atomic_add(&s.hdr->mem_top, s.cnt[i]);
+                s.fillp[i] = 0;
+            }
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            uint32_t r = s.root[i];
+            if (s.comp_dirty[r]) {
+                uint32_t p = cb_atomic_add(&s.fillp[r], 1);
+                s.members[s.start[r] + p] = i;
+            }
+            s.dirty[i] = 0;
+        }
+        g.sync();
+        const uint32_t ncomp = s.hdr->ncomp;
+        for (uint32_t c = g.tid; c < ncomp; c += g.n) solve_component(s, c);
+        g.sync();
+        const uint32_t st = s.hdr->status;
+        const uint32_t ngrow = s.hdr->ngrow;
+        g.sync();  // everyone has read the verdict before the next phase may change it
+        if (st) return round;
+        if (ngrow == 0) return round;
+        for (uint32_t k = g.tid; k < ngrow; k += g.n) {
+            uint32_t ev = s.grow_ev[k];
+            explore_event(s, ev, s.grow_to[k], s.nb_cnt[ev]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Matched pair -> graph edges along the canonical shortest path: among equal-length paths, walking back from the
+// larger event index towards the smaller one always steps to the smallest-id tight predecessor. Stored as the node
+// sequence src .. dst in the dynamic region.
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD void extract_path(Shot &s, uint32_t i, uint32_t j, int64_t d_total) {
+    DijkScratch &dj = s.dj;
+    const uint32_t src = s.event_node(i), dst = s.event_node(j);
+    bool ok = true;
+    uint32_t k0 = ht_slot(dj, src);
+    dj.dist[k0] = 0;
+    heap_push(dj, 0, src);
+    while (dj.hsize) {
+        int64_t d;
+        uint32_t u;
+        heap_pop(dj, &d, &u);
+        if (d != ht_get(dj, u)) continue;
+        if (u == dst) break;  // every node closer than d_total is settled; weights are positive
+        const uint32_t e1 = s.T.row_ptr[u + 1];
+        for (uint32_t e = s.T.row_ptr[u]; e < e1; e++) {
+            AdjEntry a = s.T.adj[e];
+            int64_t nd = d + a.wt;
+            if (nd > d_total) continue;
+            uint32_t k = ht_slot(dj, a.nbr);
+            if (k == HT_EMPTY) { ok = false; break; }
+            int64_t od = dj.dist[k];
+            if (od < 0 || nd < od) {
+                dj.dist[k] = nd;
+                if (!heap_push(dj, nd, a.nbr)) { ok = false; break; }
+            }
+        }
+        if (!ok) break;
+    }
+    uint32_t len = 0;
+    uint32_t *out = nullptr;
+    if (ok) {
+        // two walks: count, then fill back to front
+        for (int pass = 0; pass < 2 && ok; pass++) {
+            uint32_t cur = dst;
+            int64_t dc = d_total;
+            uint32_t pos = len;
+            if (pass == 1) out[--pos] = cur;
+            else len = 1;
+            while (cur != src) {
+                uint32_t best = NO_INDEX;
+                int64_t bd = 0;
+                const uint32_t e1 = s.T.row_ptr[cur + 1];
+                for (uint32_t e = s.T.row_ptr[cur]; e < e1; e++) {
+                    AdjEntry a = s.T.adj[e];
+                    int64_t dv = ht_get(dj, a.nbr);
+                    if (dv >= 0 && dv + a.wt == dc) {
+                        best = a.nbr;
+                        bd = dv;
+                        break;
+                    }
+                }
+                if (best == NO_INDEX) { ok = false; break; }
+                cur = best;
+                dc = bd;
+                if (pass == 1) out[--pos] = cur;
+                else len++;
+            }
+            if (pass == 0 && ok) {
+                out = (uint32_t *)s.alloc(uint64_t{len} * 4);
+                if (!out) { ok = false; ht_clear(dj); return; }
+            }
+        }
+    }
+    ht_clear(dj);
+    if (!ok) {
+        s.fail(SHOT_SCRATCH_OVERFLOW);
+        return;
+    }
+    s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
+    s.path_len[i] = len;
+}
+
+template <class G>
+CB_HD void paths_shot(Shot &s, const G &g) {
+    uint64_t wsum = 0;
+    for (uint32_t i = g.tid; i < s.M; i += g.n) {
+        int32_t j = s.partner[i];
+        s.path_len[i] = 0;
+        if (j > (int32_t)i) {
+            int64_t d = seen_distance(s, i, (uint32_t)j);
+            wsum += (uint64_t)d;
+            extract_path(s, i, (uint32_t)j, d);
+        }
+    }
+    if (wsum) cb_atomic_add64(&s.hdr->weight, wsum);
+    g.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stages 3 + 4, one thread per shot: Euler tours (graph/euler_tours.h:89-112, euler_tours.cc:21-97) over
+// matched edges + one doubling edge per detection event, each closed tour discharged through the drag table
+// (decode/decoder.cc:80-203) and XOR-ed into the prediction (decoder.cc:268-276).
+// ---------------------------------------------------------------------------------------------------------------
+struct OptMask {
+    uint64_t v[4];
+    uint32_t has;  // bit c set <=> state c holds a value
+};
+
+CB_HD uint32_t find_half_edge(const TablesView &T, uint32_t from, uint32_t to) {
+    for (uint32_t e = T.row_ptr[from]; e < T.row_ptr[from + 1]; e++)
+        if (T.adj[e].nbr == to) return e;
+    return NO_INDEX;
+}
+
+// decoder.cc:80-138. `used` bookkeeping is a per-detection-event flag instead of a linear search.
+CB_HD bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len, uint32_t start, uint64_t *out) {
+    OptMask cur;
+    cur.has = 1u << start;
+    cur.v[0] = cur.v[1] = cur.v[2] = cur.v[3] = 0;
+    uint32_t cur_node = cycle[len - 1];
+    uint32_t cur_loc = cur_node >> 1;
+    for (uint32_t k = 0; k < len; k++) {
+        uint32_t next_node = cycle[k];
+        uint32_t next_loc = next_node >> 1;
+        bool has_event = s.node_is_event(cur_node);
+        uint32_t evi = has_event ? (s.node_event_index(cur_node) >> 1) : 0;
+        OptMask after;
+        after.has = 0;
+        after.v[0] = after.v[1] = after.v[2] = after.v[3] = 0;
+        if (next_loc == cur_loc && has_event && !s.used_flag[evi]) {
+            s.used_flag[evi] = 1;
+            uint8_t info = s.T.det_info[cur_loc];
+            uint32_t dc = info & DET_COLOR_MASK;
+            if (cur.has & 1u) { after.v[dc] = cur.v[0]; after.has |= 1u << dc; }
+            if (cur.has & (1u << dc)) { after.v[0] = cur.v[dc]; after.has |= 1u; }
+            if (dc == 0) {
+                // unreachable for valid tables (events never sit on NEUTRAL detectors); mirror optional semantics:
+                // after[dc] = cur[NEUTRAL]; after[NEUTRAL] = cur[dc] with dc == NEUTRAL keeps cur[NEUTRAL].
+            }
+            if (info & DET_REP_WEIGHT3) {
+                uint32_t c1 = dc % 3 + 1, c2 = c1 % 3 + 1;
+                uint64_t f = s.T.rep_obs[cur_loc];
+                if (cur.has & (1u << c1)) { after.v[c2] = cur.v[c1] ^ f; after.has |= 1u << c2; }
+                if (cur.has & (1u << c2)) { after.v[c1] = cur.v[c2] ^ f; after.has |= 1u << c1; }
+            }
+        } else {
+            uint32_t di = NO_INDEX;
+            bool forward = true;  // walking the stored (min, max) orientation
+            if (cur_loc == next_loc) {
+                di = s.T.self_drag[cur_loc];
+            } else {
+                uint32_t e = find_half_edge(s.T, cur_node, next_node);
+                if (e != NO_INDEX) di = s.T.adj_drag[e];
+                forward = cur_loc < next_loc;
+            }
+            if (di != NO_INDEX) {
+                const DragEntry &de = s.T.drag[di];
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    if (!(cur.has & (1u << cc))) continue;
+                    for (uint32_t nc = 0; nc < 4; nc++) {
+                        uint32_t bit = forward ? 4 * cc + nc : 4 * nc + cc;
+                        if (de.valid & (1u << bit)) {
+                            after.v[nc] = cur.v[cc] ^ de.obs[bit];
+                            after.has |= 1u << nc;
+                        }
+                    }
+                }
+            }
+        }
+        cur = after;
+        cur_node = next_node;
+        cur_loc = next_loc;
+    }
+    // reset the used flags touched by this attempt
+    for (uint32_t k = 0; k < len; k++) {
+        uint32_t nd = cycle[k];
+        if (s.node_is_event(nd)) s.used_flag[s.node_event_index(nd) >> 1] = 0;
+    }
+    if (cur.has & (1u << start)) {
+        *out = cur.v[start];
+        return true;
+    }
+    return false;
+}
+
+struct HalfEdge {
+    uint32_t node;   // NO_INDEX = voided
+    uint32_t back;   // position of the reverse half-edge in the other node's list
+};
+
+// Runs on one thread. Returns false after setting the status on failure.
+CB_HD bool lift_shot(Shot &s, uint64_t *obs_out, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
+    const uint32_t M = s.M;
+    // count edges
+    uint32_t nedges = M / 2;
+    for (uint32_t i = 0; i < M; i++)
+        if (s.path_len[i]) nedges += s.path_len[i] - 1;
+    uint32_t *slot_node = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);   // local id -> node
+    uint32_t *deg = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);         // then: list start
+    uint32_t *fill = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);        // then: next_neighbor cursor
+    uint32_t *lend = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);
+    HalfEdge *he = (HalfEdge *)s.alloc(uint64_t{nedges} * 2 * sizeof(HalfEdge) + 16);
+    uint32_t *cyc = (uint32_t *)s.alloc((uint64_t{nedges} + 4) * 4);
+    if (!slot_node || !deg || !fill || !lend || !he || !cyc) return false;
+    uint32_t nslots = 0;
+    auto slot_of = [&](uint32_t node) -> uint32_t {
+        uint32_t k = s.node_slot[node];
+        if (k == NO_INDEX) {
+            k = nslots++;
+            s.node_slot[node] = k;
+            slot_node[k] = node;
+            deg[k] = 0;
+        }
+        return k;
+    };
+    // pass 1: degrees (matched edges in emission order, then doubling edges)
+    for (uint32_t i = 0; i < M; i++) {
+        uint32_t len = s.path_len[i];
+        if (!len) continue;
+        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+        for (uint32_t k = 0; k + 1 < len; k++) {
+            deg[slot_of(p[k])]++;
+            deg[slot_of(p[k + 1])]++;
+        }
+    }
+    for (uint32_t i = 0; i < M; i += 2) {
+        deg[slot_of(s.event_node(i))]++;
+        deg[slot_of(s.event_node(i + 1))]++;
+    }
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < nslots; k++) {
+        uint32_t dg = deg[k];
+        deg[k] = run;       // list start
+        fill[k] = run;      // insertion cursor
+        run += dg;
+        lend[k] = run;
+    }
+    uint64_t dumped = 0;
+    auto add_edge = [&](uint32_t a, uint32_t b) {
+        uint32_t sa = s.node_slot[a], sb = s.node_slot[b];
+        uint32_t pa_ = fill[sa]++, pb_ = fill[sb]++;
+        he[pa_].node = b;
+        he[pa_].back = pb_;
+        he[pb_].node = a;
+        he[pb_].back = pa_;
+    };
+    for (uint32_t i = 0; i < M; i++) {
+        uint32_t len = s.path_len[i];
+        if (!len) continue;
+        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+        for (uint32_t k = 0; k + 1 < len; k++) {
+            add_edge(p[k], p[k + 1]);
+            if (edge_dump) {
+                if (dumped + 2 <= edge_dump_cap) {
+                    edge_dump[dumped] = p[k];
+                    edge_dump[dumped + 1] = p[k + 1];
+                }
+                dumped += 2;
+            }
+        }
+    }
+    if (edge_dump_len) *edge_dump_len = dumped;
+    for (uint32_t i = 0; i < M; i += 2) add_edge(s.event_node(i), s.event_node(i + 1));
+    // cursors restart at the list heads (next_neighbor = 0)
+    for (uint32_t k = 0; k < nslots; k++) fill[k] = deg[k];
+    auto look_next = [&](uint32_t sl) -> uint32_t {  // euler_tours.cc:34-45
+        while (true) {
+            if (fill[sl] >= lend[sl]) return NO_INDEX;
+            if (he[fill[sl]].node == NO_INDEX) {
+                fill[sl]++;
+                continue;
+            }
+            return fill[sl];
+        }
+    };
+    uint64_t solution = 0;
+    bool ok = true;
+    uint32_t code = 0;
+    // burn components in matched-edge-list order (euler_tours.h:104-106)
+    for (uint32_t i = 0; i < M && ok; i++) {
+        uint32_t len = s.path_len[i];
+        if (!len) continue;
+        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+        for (uint32_t k = 0; k + 1 < len && ok; k++) {
+            for (uint32_t side = 0; side < 2 && ok; side++) {
+                uint32_t n0 = p[k + side];
+                if (look_next(s.node_slot[n0]) == NO_INDEX) continue;
+                uint32_t clen = 0;
+                cyc[clen++] = n0;
+                while (true) {
+                    // extend_cycle_depth_first (euler_tours.cc:64-76)
+                    while (true) {
+                        uint32_t sl = s.node_slot[cyc[clen - 1]];
+                        uint32_t h = look_next(sl);
+                        if (h == NO_INDEX) break;
+                        fill[sl]++;
+                        HalfEdge e = he[h];
+                        cyc[clen++] = e.node;
+                        he[e.back].node = NO_INDEX;
+                    }
+                    // rotate_cycle_to_end_with_unfinished_node (euler_tours.cc:78-97)
+                    if (cyc[clen - 1] != cyc[0]) {
+                        ok = false;
+                        code = SHOT_EULER_FAILED;
+                        break;
+                    }
+                    clen--;
+                    uint32_t ck = 1;
+                    while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
+                    if (ck >= clen) break;
+                    // cyc = cyc[ck:] + cyc[:ck+1]
+                    for (uint32_t a = 0, b = ck - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+                    for (uint32_t a = ck, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+                    for (uint32_t a = 0, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+                    cyc[clen] = cyc[0];
+                    clen++;
+                }
+                if (!ok) break;
+                // discharge_cycle (decoder.cc:140-203): start charges N, R, G, B; first that closes wins
+                bool lifted = false;
+                for (uint32_t c = 0; c < 4 && !lifted; c++) {
+                    uint64_t v;
+                    if (discharge_single_start(s, cyc, clen, c, &v)) {
+                        solution ^= v;
+                        lifted = true;
+                    }
+                }
+                if (!lifted) {
+                    ok = false;
+                    code = SHOT_DISCHARGE_FAILED;
+                }
+            }
+        }
+    }
+    for (uint32_t k = 0; k < nslots; k++) s.node_slot[slot_node[k]] = NO_INDEX;
+    if (!ok) {
+        s.fail(code);
+        return false;
+    }
+    *obs_out = solution;
+    return true;
+}
+
+// One shot, start to finish. `shot` indexes the caller's arrays.
+template <class G>
+CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g) {
+    ingest_shot(s, p.dets + (uint64_t)shot * p.stride, g);
+    uint32_t rounds = 0;
+    if (!s.hdr->status && s.M) {
+        rounds = match_shot(s, g);
+        if (!s.hdr->status) paths_shot(s, g);
+    }
+    g.sync();
+    if (g.tid == 0) {
+        uint64_t obs = 0;
+        if (!s.hdr->status && s.M) lift_shot(s, &obs, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
+        else if (p.edge_dump_len) *p.edge_dump_len = 0;
+        uint32_t st = s.hdr->status;
+        p.status_out[shot] = st;
+        p.obs_out[shot] = st ? 0 : obs;
+        if (p.weight_out) p.weight_out[shot] = st ? 0 : (int64_t)s.hdr->weight;
+        if (p.rounds_out) p.rounds_out[shot] = rounds;
+    }
+    g.sync();
+}
+
+}  // namespace cb200
+
+#endif

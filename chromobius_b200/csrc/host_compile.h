@@ -1,0 +1,95 @@
+// Host side of the decoder: DEM text -> flat tables (runs once per DEM, never on the GPU).
+// Mirrors the reference's Decoder::from_dem pipeline (src/chromobius/decode/decoder.cc:24-69).
+#ifndef CHROMOBIUS_B200_HOST_COMPILE_H
+#define CHROMOBIUS_B200_HOST_COMPILE_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tables.h"
+
+namespace cb200 {
+
+// A DEM error after `repeat` unrolling and `shift_detectors` application.
+struct FlatDemError {
+    double p;
+    uint32_t first_target;  // into FlatDem::targets
+    uint32_t num_targets;
+    uint32_t line;          // source line, for messages
+};
+// Target encoding: detector d -> d ; observable k -> OBS_FLAG | k ; separator -> SEPARATOR
+constexpr uint64_t TGT_OBS_FLAG = 1ull << 62;
+constexpr uint64_t TGT_SEPARATOR = 1ull << 63;
+
+struct FlatDetector {
+    uint64_t id;
+    uint32_t num_coords;
+    double coords[8];       // shifted; only the first 8 are kept
+    uint32_t line;
+};
+
+struct FlatDem {
+    uint64_t num_detectors = 0;
+    uint64_t num_observables = 0;
+    std::vector<FlatDemError> errors;
+    std::vector<uint64_t> targets;
+    std::vector<FlatDetector> detectors;
+    std::vector<std::string> lines;  // trimmed source lines for error messages
+
+    // Throws std::invalid_argument on malformed text.
+    static FlatDem parse(const std::string &text);
+};
+
+struct MobiusDemError {
+    double p;
+    uint32_t first_edge;  // into HostTables::mobius_edges (pairs)
+    uint32_t num_edges;
+};
+
+struct RgbRep {
+    uint32_t node[3];  // red, green, blue (NO_INDEX if absent)
+    uint64_t obs_flip;
+    uint8_t charge_flip;
+};
+
+struct HostTables {
+    uint32_t num_dets = 0;
+    uint32_t num_obs = 0;
+    double normalising_constant = 1.0;
+
+    // Reference-shaped intermediate results (kept for describe_decoder and for parity tests).
+    std::vector<uint8_t> color, basis, ignored;            // node_colors
+    std::vector<uint32_t> atom_dets;                        // 3 per atomic error (NO_INDEX padded), map order
+    std::vector<uint64_t> atom_obs;
+    std::vector<MobiusDemError> mobius_errors;
+    std::vector<uint32_t> mobius_edges;                     // interleaved pairs
+    std::vector<RgbRep> rgb_reps;
+    std::vector<std::vector<std::pair<uint32_t, uint64_t>>> charge_graph;  // per node, sorted by neighbour
+    uint64_t drag_ambiguities = 0;
+
+    // Device-shaped tables.
+    std::vector<uint32_t> row_ptr;
+    std::vector<AdjEntry> adj;
+    std::vector<uint32_t> adj_drag;
+    std::vector<uint8_t> det_info;
+    std::vector<uint64_t> rep_obs;
+    std::vector<uint32_t> self_drag;
+    std::vector<uint8_t> ingest_mask;
+    std::vector<DragEntry> drag;
+    std::vector<uint32_t> drag_pair;  // (n1, n2) per DragEntry, n1 <= n2
+
+    TablesView view() const;
+
+    // Same text layout as the reference's `chromobius describe_decoder` for the charge graph, rgb reps and
+    // drag graph sections (decode/decoder.cc:279-291); the Moebius DEM is printed as plain `error(p) Da Db ^ ...` lines.
+    std::string describe() const;
+    std::string mobius_dem_text() const;
+};
+
+// Throws std::invalid_argument with the reference's messages where tests pin them.
+HostTables compile_tables(const FlatDem &dem);
+
+}  // namespace cb200
+
+#endif

@@ -1,0 +1,76 @@
+// Host "simulation" build of the device decode path (chromobius_b200/csrc/decode_core.h) with a group of one thread.
+// TEST INFRASTRUCTURE ONLY: lets the CPU-only test tier exercise the exact per-shot logic the CUDA kernels run.
+// The product library never links or loads this file.
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../chromobius_b200/csrc/decode_core.h"
+#include "../../chromobius_b200/csrc/host_compile.h"
+
+using namespace cb200;
+
+struct Sim {
+    HostTables tables;
+    std::vector<uint8_t> arena;
+    ScratchConfig cfg{};
+};
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char *cbsim_last_error() { return g_err.c_str(); }
+
+void *cbsim_compile(const char *dem_text) {
+    try {
+        auto *s = new Sim();
+        s->tables = compile_tables(FlatDem::parse(dem_text));
+        return s;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void cbsim_free(void *h) { delete (Sim *)h; }
+uint64_t cbsim_num_detectors(void *h) { return ((Sim *)h)->tables.num_dets; }
+uint64_t cbsim_num_observables(void *h) { return ((Sim *)h)->tables.num_obs; }
+
+// Decodes shots one by one. Returns 0. status_out[k] != 0 marks failed shots.
+// edges_out (nullable): matched edges of the LAST shot (interleaved), *num_edge_ints receives the count.
+int cbsim_decode(void *h, const uint8_t *dets, uint64_t num_shots, uint64_t stride, uint64_t *obs_out, int64_t *weight_out,
+                 uint32_t *status_out, uint32_t *rounds_out, uint32_t ht_log2, uint64_t dyn_bytes, int64_t *edges_out,
+                 uint64_t edges_cap, uint64_t *num_edge_ints) {
+    auto *s = (Sim *)h;
+    DecodeParams p{};
+    p.T = s->tables.view();
+    p.dets = dets;
+    p.stride = stride;
+    p.num_shots = (uint32_t)num_shots;
+    p.obs_out = obs_out;
+    p.weight_out = weight_out;
+    p.status_out = status_out;
+    p.rounds_out = rounds_out;
+    p.edge_dump = edges_out;
+    p.edge_dump_cap = edges_cap;
+    p.edge_dump_len = num_edge_ints;
+    p.cfg.ht_log2 = ht_log2;
+    p.cfg.heap_cap = 2u << ht_log2;
+    p.cfg.found_cap = 256;
+    p.cfg.max_events = 2 * s->tables.num_dets + 2;
+    p.cfg.dyn_bytes = dyn_bytes;
+    uint64_t bytes = arena_bytes_per_group(p.cfg, p.T.num_nodes, 1);
+    s->arena.assign(bytes, 0);
+    p.arena = s->arena.data();
+    p.arena_stride = bytes;
+    HostGroup g;
+    Shot shot;
+    bind_shot(shot, p, p.arena, g);
+    init_group_arena(shot, g);
+    for (uint32_t k = 0; k < num_shots; k++) decode_shot(shot, p, k, g);
+    return 0;
+}
+
+}  // extern "C"
