@@ -1,0 +1,610 @@
+// CUDA kernels (sm_100a) and the C ABI of the B200 decoder. See include/chromobius_b200.h for the boundary and
+// decode_core.h for the per-shot algorithm. No PyTorch, no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/chromobius_b200.h"
+#include "decode_core.h"
+#include "host_compile.h"
+
+using namespace cb200;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define CUDA_CHECK(expr)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t e_ = (expr);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" +  \
+                            std::to_string(__LINE__) + ")");                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device groups
+// ---------------------------------------------------------------------------------------------------------------
+template <int GROUP>
+struct DevGroup {
+    int tid;
+    int n;
+    __device__ __forceinline__ void sync() const {
+        if (GROUP == 1) {
+        } else if (GROUP == 32) {
+            __syncwarp();
+        } else {
+            __syncthreads();
+        }
+    }
+};
+
+constexpr int BLOCK_THREADS = 128;
+
+template <int GROUP>
+__device__ __forceinline__ void group_ids(uint32_t &group, DevGroup<GROUP> &g) {
+    if (GROUP == 1) {
+        group = blockIdx.x * blockDim.x + threadIdx.x;
+        g.tid = 0;
+        g.n = 1;
+    } else if (GROUP == 32) {
+        group = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+        g.tid = threadIdx.x & 31;
+        g.n = 32;
+    } else {
+        group = blockIdx.x;
+        g.tid = threadIdx.x;
+        g.n = blockDim.x;
+    }
+}
+
+// K0: establishes the persistent-clean invariants of every group's arena.
+template <int GROUP>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_init_arena(DecodeParams p, uint32_t num_groups) {
+    uint32_t group;
+    DevGroup<GROUP> g;
+    group_ids<GROUP>(group, g);
+    if (group >= num_groups) return;
+    Shot s;
+    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, g);
+    init_group_arena(s, g);
+}
+
+// K1: bit-packed ingest statistics. One warp per shot: masked popcount of the row with coalesced loads.
+// Emits per-shot detection-event counts, the batch maximum and the batch total.
+__global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict__ dets, uint64_t stride, uint32_t num_shots,
+                                                      const uint8_t *__restrict__ mask, uint32_t num_det_bytes,
+                                                      uint32_t *__restrict__ counts, uint32_t *__restrict__ max_count,
+                                                      unsigned long long *__restrict__ total) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t local_max = 0;
+    unsigned long long local_total = 0;
+    for (uint32_t shot = warp; shot < num_shots; shot += nwarps) {
+        const uint8_t *row = dets + (uint64_t)shot * stride;
+        uint32_t c = 0;
+        // head bytes up to 16-byte alignment, 16-byte body, tail bytes
+        uint32_t head = (uint32_t)((16 - ((uintptr_t)row & 15)) & 15);
+        if (head > num_det_bytes) head = num_det_bytes;
+        uint32_t body = (num_det_bytes - head) / 16;
+        for (uint32_t k = lane; k < head; k += 32) c += __popc((uint32_t)(row[k] & mask[k]));
+        const uint4 *row16 = (const uint4 *)(row + head);
+        for (uint32_t k = lane; k < body; k += 32) {
+            uint4 v = row16[k];
+            const uint8_t *m = mask + head + 16 * k;  // mask is small and L1/L2 resident; unaligned -> byte loads
+            uint32_t m0 = m[0] | (m[1] << 8) | (m[2] << 16) | ((uint32_t)m[3] << 24);
+            uint32_t m1 = m[4] | (m[5] << 8) | (m[6] << 16) | ((uint32_t)m[7] << 24);
+            uint32_t m2 = m[8] | (m[9] << 8) | (m[10] << 16) | ((uint32_t)m[11] << 24);
+            uint32_t m3 = m[12] | (m[13] << 8) | (m[14] << 16) | ((uint32_t)m[15] << 24);
+            c += __popc(v.x & m0) + __popc(v.y & m1) + __popc(v.z & m2) + __popc(v.w & m3);
+        }
+        for (uint32_t k = head + 16 * body + lane; k < num_det_bytes; k += 32) c += __popc((uint32_t)(row[k] & mask[k]));
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if (lane == 0) {
+            counts[shot] = c;
+            local_max = max(local_max, c);
+            local_total += c;
+        }
+    }
+    if (lane == 0 && local_total) {
+        atomicMax(max_count, local_max);
+        atomicAdd(total, local_total);
+    }
+}
+
+// K2: the decode kernel. Persistent groups pull shots from a queue.
+template <int GROUP>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_decode(DecodeParams p, uint32_t num_groups) {
+    uint32_t group;
+    DevGroup<GROUP> g;
+    group_ids<GROUP>(group, g);
+    if (group >= num_groups) return;
+    Shot s;
+    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, g);
+    const uint32_t total = p.shot_list ? p.list_len : p.num_shots;
+    while (true) {
+        if (g.tid == 0) s.hdr->pad[0] = atomicAdd(p.work_counter, 1u);
+        g.sync();
+        uint32_t k = s.hdr->pad[0];
+        g.sync();
+        if (k >= total) break;
+        uint32_t shot = p.shot_list ? p.shot_list[k] : k;
+        decode_shot(s, p, shot, g);
+    }
+}
+
+// K3: u64 masks -> little-endian observable bytes, integer weights -> float32 (decode/pymatcher.cc:40).
+__global__ void k_finish(const uint64_t *__restrict__ obs64, const int64_t *__restrict__ wint, uint32_t num_shots,
+                         uint32_t obs_bytes, double inv_norm, uint8_t *__restrict__ obs_out, float *__restrict__ w_out,
+                         int64_t *__restrict__ wint_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_shots) return;
+    uint64_t m = obs64[i];
+    for (uint32_t b = 0; b < obs_bytes; b++) obs_out[(uint64_t)i * obs_bytes + b] = (uint8_t)(m >> (8 * b));
+    if (w_out) w_out[i] = (float)((double)wint[i] * inv_norm);
+    if (wint_out) wint_out[i] = wint[i];
+}
+
+template <class T>
+struct DeviceBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        CUDA_CHECK(cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T)));
+        cap = n;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct cb200_decoder {
+    HostTables host;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // device tables
+    DeviceBuf<uint32_t> d_row_ptr, d_adj_drag, d_self_drag;
+    DeviceBuf<AdjEntry> d_adj;
+    DeviceBuf<uint8_t> d_det_info, d_ingest_mask;
+    DeviceBuf<uint64_t> d_rep_obs;
+    DeviceBuf<DragEntry> d_drag;
+    TablesView dview{};
+    uint64_t table_bytes = 0;
+    // per-call buffers (grow only)
+    DeviceBuf<uint8_t> d_dets, d_obs_bytes, d_arena;
+    DeviceBuf<uint64_t> d_obs64;
+    DeviceBuf<int64_t> d_wint, d_wint_out, d_edges;
+    DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list;
+    DeviceBuf<float> d_wfloat;
+    // arena layout currently initialised on the device
+    ScratchConfig arena_cfg{};
+    uint32_t arena_group = 0, arena_groups = 0;
+    uint64_t arena_stride = 0;
+    // tuning
+    uint32_t tune_group = 0, tune_ht_log2 = 0;
+};
+
+namespace {
+
+void upload_tables(cb200_decoder *d) {
+    const HostTables &h = d->host;
+    auto up = [&](auto &buf, const auto &vec) {
+        buf.ensure(vec.size());
+        if (!vec.empty()) CUDA_CHECK(cudaMemcpy(buf.ptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+        d->table_bytes += vec.size() * sizeof(vec[0]);
+    };
+    up(d->d_row_ptr, h.row_ptr);
+    up(d->d_adj, h.adj);
+    up(d->d_adj_drag, h.adj_drag);
+    up(d->d_det_info, h.det_info);
+    up(d->d_rep_obs, h.rep_obs);
+    up(d->d_self_drag, h.self_drag);
+    up(d->d_ingest_mask, h.ingest_mask);
+    up(d->d_drag, h.drag);
+    TablesView v = h.view();
+    v.row_ptr = d->d_row_ptr.ptr;
+    v.adj = d->d_adj.ptr;
+    v.adj_drag = d->d_adj_drag.ptr;
+    v.det_info = d->d_det_info.ptr;
+    v.rep_obs = d->d_rep_obs.ptr;
+    v.self_drag = d->d_self_drag.ptr;
+    v.ingest_mask = d->d_ingest_mask.ptr;
+    v.drag = d->d_drag.ptr;
+    d->dview = v;
+}
+
+template <int GROUP>
+void launch_init(const DecodeParams &p, uint32_t groups, cudaStream_t st) {
+    uint32_t per_block = GROUP == 1 ? BLOCK_THREADS : (GROUP == 32 ? BLOCK_THREADS / 32 : 1);
+    uint32_t blocks = (groups + per_block - 1) / per_block;
+    k_init_arena<GROUP><<<blocks, BLOCK_THREADS, 0, st>>>(p, groups);
+}
+template <int GROUP>
+void launch_decode(const DecodeParams &p, uint32_t groups, cudaStream_t st) {
+    uint32_t per_block = GROUP == 1 ? BLOCK_THREADS : (GROUP == 32 ? BLOCK_THREADS / 32 : 1);
+    uint32_t blocks = (groups + per_block - 1) / per_block;
+    k_decode<GROUP><<<blocks, BLOCK_THREADS, 0, st>>>(p, groups);
+}
+
+const char *status_message(uint32_t st) {
+    switch (st) {
+        case SHOT_SCRATCH_OVERFLOW: return "decoder scratch memory exhausted even after enlarging it";
+        case SHOT_NO_PERFECT_MATCHING: return "No perfect matching exists for the detection events.";
+        case SHOT_EULER_FAILED: return "Graph didn't decompose into Euler tours.";
+        case SHOT_DISCHARGE_FAILED:
+            return "Failed to lift a flattened edge cycle from the matcher into an explanation of the detection events in "
+                   "the cycle.\nThis error could be due to a coloring error in the model used to configure the decoder, or a "
+                   "bug in the decoder.";
+        case SHOT_ROUND_LIMIT: return "certified matching did not converge within the round limit";
+        case SHOT_COMPONENT_TOO_LARGE: return "a matching component exceeded the supported size";
+        default: return "unknown failure";
+    }
+}
+
+// Chooses the group width and scratch configuration for a batch and (re)initialises the arena when the layout changes.
+struct Plan {
+    uint32_t group;
+    uint32_t groups;
+    ScratchConfig cfg;
+};
+
+Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, double mean_det_events, uint32_t escalation) {
+    Plan pl{};
+    uint32_t group = d->tune_group;
+    if (group == 0) group = mean_det_events >= 24 ? 128 : 32;
+    if (group != 1 && group != 32 && group != 128) group = 32;
+    pl.group = group;
+    uint32_t ht = d->tune_ht_log2 ? d->tune_ht_log2 : 10;
+    ht += 3 * escalation;
+    uint32_t full = 1;
+    while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
+    if (ht > full) ht = full;
+    pl.cfg.ht_log2 = ht;
+    pl.cfg.heap_cap = 2u << ht;
+    pl.cfg.found_cap = 64u << (2 * escalation);
+    pl.cfg.max_events = std::max<uint32_t>(2 * max_det_events, 2);
+    pl.cfg.dyn_bytes = ((uint64_t)(64 << 10) + (uint64_t)3072 * pl.cfg.max_events) << (3 * escalation);
+    uint32_t per_sm = group == 1 ? 256 : (group == 32 ? 16 : 4);
+    uint64_t want = (uint64_t)d->num_sms * per_sm;
+    if (escalation) want = std::min<uint64_t>(want, 64);
+    pl.groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, work_items));
+    return pl;
+}
+
+void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &launches) {
+    uint64_t stride = arena_bytes_per_group(pl.cfg, d->dview.num_nodes, pl.group);
+    bool same = d->arena_group == pl.group && d->arena_stride == stride && d->arena_groups >= pl.groups &&
+                memcmp(&d->arena_cfg, &pl.cfg, sizeof(ScratchConfig)) == 0;
+    p.cfg = pl.cfg;
+    p.arena_stride = stride;
+    if (!same) {
+        d->d_arena.ensure(stride * pl.groups);
+        p.arena = d->d_arena.ptr;
+        if (pl.group == 1) launch_init<1>(p, pl.groups, d->stream);
+        else if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
+        else launch_init<128>(p, pl.groups, d->stream);
+        CUDA_CHECK(cudaGetLastError());
+        launches++;
+        d->arena_group = pl.group;
+        d->arena_stride = stride;
+        d->arena_groups = pl.groups;
+        d->arena_cfg = pl.cfg;
+    }
+    p.arena = d->d_arena.ptr;
+}
+
+int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
+                float *weight_out, int64_t *weight_int_out, uint32_t flags, cb200_batch_stats *stats, int64_t *edges_out,
+                uint64_t edges_cap, uint64_t *num_edge_ints, uint64_t *obs_mask_out) {
+    cb200_batch_stats st{};
+    st.first_failed_shot = -1;
+    st.num_shots = num_shots;
+    if (stats) *stats = st;
+    if (num_shots == 0) return CB200_OK;
+    if (num_shots > 0x7FFFFFF0ull) throw std::invalid_argument("too many shots in one batch (limit 2^31 - 16)");
+    const uint32_t nb = d->dview.num_det_bytes;
+    const uint32_t ob = (d->dview.num_obs + 7) / 8;
+    if (row_stride < nb) throw std::invalid_argument("row_stride is smaller than the number of detector bytes");
+    CUDA_CHECK(cudaSetDevice(d->device));
+    const bool dev_io = (flags & CB200_IO_DEVICE) != 0;
+    const uint32_t n = (uint32_t)num_shots;
+    cudaStream_t s = d->stream;
+    uint64_t launches = 0;
+
+    CUDA_CHECK(cudaEventRecord(d->ev[0], s));
+    const uint8_t *d_dets = dets;
+    uint64_t d_stride = row_stride;
+    if (!dev_io) {
+        if (nb) {
+            d->d_dets.ensure((size_t)n * nb);
+            CUDA_CHECK(cudaMemcpy2DAsync(d->d_dets.ptr, nb, dets, row_stride, nb, n, cudaMemcpyHostToDevice, s));
+        }
+        d_dets = d->d_dets.ptr;
+        d_stride = nb;
+    }
+    CUDA_CHECK(cudaEventRecord(d->ev[1], s));
+
+    d->d_obs64.ensure(n);
+    d->d_wint.ensure(n);
+    d->d_status.ensure(n);
+    d->d_rounds.ensure(n);
+    d->d_counts.ensure(n);
+    d->d_scalars.ensure(8);
+    CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr, 0, 8 * sizeof(uint32_t), s));
+    // scalars: [0] max count, [2..3] total (u64), [4] work counter
+    {
+        uint32_t blocks = std::min<uint32_t>((n + 7) / 8, (uint32_t)d->num_sms * 8);
+        k_count_events<<<blocks, 256, 0, s>>>(d_dets, d_stride, n, d->dview.ingest_mask, nb, d->d_counts.ptr, d->d_scalars.ptr,
+                                              (unsigned long long *)(d->d_scalars.ptr + 2));
+        CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    uint32_t scal[8];
+    CUDA_CHECK(cudaMemcpyAsync(scal, d->d_scalars.ptr, sizeof(scal), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaEventRecord(d->ev[2], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    uint32_t max_count = scal[0];
+    uint64_t total_events;
+    memcpy(&total_events, &scal[2], 8);
+    st.num_detection_events = total_events;
+    st.max_events_per_shot = 2 * max_count;
+
+    DecodeParams p{};
+    p.T = d->dview;
+    p.dets = d_dets;
+    p.stride = d_stride;
+    p.num_shots = n;
+    p.obs_out = d->d_obs64.ptr;
+    p.weight_out = d->d_wint.ptr;
+    p.status_out = d->d_status.ptr;
+    p.rounds_out = d->d_rounds.ptr;
+    p.work_counter = d->d_scalars.ptr + 4;
+    if (edges_out || num_edge_ints) {
+        d->d_edges.ensure(edges_cap + 2);
+        p.edge_dump = d->d_edges.ptr;
+        p.edge_dump_cap = edges_cap;
+        p.edge_dump_len = (uint64_t *)(d->d_edges.ptr + edges_cap);
+    }
+
+    std::vector<uint32_t> status(n);
+    std::vector<uint32_t> retry;
+    for (uint32_t esc = 0; esc < 4; esc++) {
+        uint64_t items = esc == 0 ? n : retry.size();
+        Plan pl = make_plan(d, items, max_count, (double)total_events / (double)n, esc);
+        ensure_arena(d, pl, p, launches);
+        if (esc == 0) {
+            st.group_threads = pl.group;
+            st.num_groups = pl.groups;
+            p.shot_list = nullptr;
+            p.list_len = 0;
+        } else {
+            d->d_list.ensure(retry.size());
+            CUDA_CHECK(cudaMemcpyAsync(d->d_list.ptr, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, s));
+            p.shot_list = d->d_list.ptr;
+            p.list_len = (uint32_t)retry.size();
+            CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr + 4, 0, 4, s));
+        }
+        if (pl.group == 1) launch_decode<1>(p, pl.groups, s);
+        else if (pl.group == 32) launch_decode<32>(p, pl.groups, s);
+        else launch_decode<128>(p, pl.groups, s);
+        CUDA_CHECK(cudaGetLastError());
+        launches++;
+        if (esc == 0) CUDA_CHECK(cudaEventRecord(d->ev[3], s));
+        CUDA_CHECK(cudaMemcpyAsync(status.data(), d->d_status.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        retry.clear();
+        for (uint32_t k = 0; k < n; k++)
+            if (status[k] == SHOT_SCRATCH_OVERFLOW) retry.push_back(k);
+        if (retry.empty()) break;
+        st.num_retried_shots += retry.size();
+    }
+    for (uint32_t k = 0; k < n; k++)
+        if (status[k]) {
+            if (st.first_failed_shot < 0) {
+                st.first_failed_shot = k;
+                st.first_failed_status = status[k];
+            }
+            st.num_failed_shots++;
+        }
+
+    // outputs
+    uint8_t *d_obs_bytes = obs_out;
+    float *d_wf = weight_out;
+    int64_t *d_wi = weight_int_out;
+    if (!dev_io) {
+        d->d_obs_bytes.ensure((size_t)n * std::max<uint32_t>(ob, 1));
+        d_obs_bytes = d->d_obs_bytes.ptr;
+        if (weight_out) {
+            d->d_wfloat.ensure(n);
+            d_wf = d->d_wfloat.ptr;
+        }
+        d_wi = nullptr;
+    }
+    k_finish<<<(n + 255) / 256, 256, 0, s>>>(d->d_obs64.ptr, d->d_wint.ptr, n, ob, 1.0 / d->host.normalising_constant,
+                                            d_obs_bytes, d_wf, d_wi);
+    CUDA_CHECK(cudaGetLastError());
+    launches++;
+    CUDA_CHECK(cudaEventRecord(d->ev[4], s));
+    if (!dev_io) {
+        if (ob && obs_out) CUDA_CHECK(cudaMemcpyAsync(obs_out, d_obs_bytes, (size_t)n * ob, cudaMemcpyDeviceToHost, s));
+        if (weight_out) CUDA_CHECK(cudaMemcpyAsync(weight_out, d_wf, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (weight_int_out) CUDA_CHECK(cudaMemcpyAsync(weight_int_out, d->d_wint.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (obs_mask_out) CUDA_CHECK(cudaMemcpyAsync(obs_mask_out, d->d_obs64.ptr, 8, cudaMemcpyDeviceToHost, s));
+    if (p.edge_dump) {
+        uint64_t need = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&need, p.edge_dump_len, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (num_edge_ints) *num_edge_ints = need;
+        uint64_t take = std::min<uint64_t>(need, edges_cap);
+        if (edges_out && take) CUDA_CHECK(cudaMemcpyAsync(edges_out, p.edge_dump, take * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (stats) {
+        std::vector<uint32_t> rounds(n);
+        CUDA_CHECK(cudaMemcpyAsync(rounds.data(), d->d_rounds.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        for (uint32_t r : rounds) st.matcher_rounds += r;
+    }
+    CUDA_CHECK(cudaEventRecord(d->ev[5], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    st.kernel_launches = launches;
+    CUDA_CHECK(cudaEventElapsedTime(&st.ms_h2d, d->ev[0], d->ev[1]));
+    CUDA_CHECK(cudaEventElapsedTime(&st.ms_count, d->ev[1], d->ev[2]));
+    CUDA_CHECK(cudaEventElapsedTime(&st.ms_decode, d->ev[2], d->ev[3]));
+    CUDA_CHECK(cudaEventElapsedTime(&st.ms_d2h, d->ev[4], d->ev[5]));
+    CUDA_CHECK(cudaEventElapsedTime(&st.ms_total, d->ev[0], d->ev[5]));
+    if (stats) *stats = st;
+    if (st.num_failed_shots) {
+        g_error = std::string(status_message(st.first_failed_status)) + " (shot " + std::to_string(st.first_failed_shot) + ")";
+        return CB200_ERR_DECODE;
+    }
+    return CB200_OK;
+}
+
+template <class F>
+int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::invalid_argument &e) {
+        g_error = e.what();
+        return CB200_ERR_INVALID_ARGUMENT;
+    } catch (const CudaError &e) {
+        g_error = e.what();
+        return CB200_ERR_CUDA;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cb200_last_error(void) { return g_error.c_str(); }
+
+int cb200_compile(const char *dem_text, int device, cb200_decoder **out) {
+    if (!out) {
+        g_error = "out must not be null";
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    cb200_decoder *d = nullptr;
+    int rc = guarded([&]() {
+        if (!dem_text) throw std::invalid_argument("dem_text must not be null");
+        d = new cb200_decoder();
+        d->host = compile_tables(FlatDem::parse(dem_text));
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw CudaError(std::string("chromobius_b200 needs a CUDA device and has no CPU fallback: ") +
+                            (e != cudaSuccess ? cudaGetErrorString(e) : "no devices found"));
+        if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
+        d->device = device;
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        for (auto &e2 : d->ev) CUDA_CHECK(cudaEventCreate(&e2));
+        upload_tables(d);
+        return CB200_OK;
+    });
+    if (rc != CB200_OK) {
+        cb200_free(d);
+        return rc;
+    }
+    *out = d;
+    return CB200_OK;
+}
+
+void cb200_free(cb200_decoder *d) {
+    if (!d) return;
+    if (d->stream) {
+        cudaSetDevice(d->device);
+        cudaStreamSynchronize(d->stream);
+    }
+    d->d_row_ptr.release(); d->d_adj_drag.release(); d->d_self_drag.release(); d->d_adj.release();
+    d->d_det_info.release(); d->d_ingest_mask.release(); d->d_rep_obs.release(); d->d_drag.release();
+    d->d_dets.release(); d->d_obs_bytes.release(); d->d_arena.release(); d->d_obs64.release(); d->d_wint.release();
+    d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();
+    d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release();
+    for (auto &e : d->ev)
+        if (e) cudaEventDestroy(e);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+uint64_t cb200_num_detectors(const cb200_decoder *d) { return d->host.num_dets; }
+uint64_t cb200_num_observables(const cb200_decoder *d) { return d->host.num_obs; }
+uint64_t cb200_num_detector_bytes(const cb200_decoder *d) { return (d->host.num_dets + 7) / 8; }
+uint64_t cb200_num_observable_bytes(const cb200_decoder *d) { return (d->host.num_obs + 7) / 8; }
+double cb200_normalising_constant(const cb200_decoder *d) { return d->host.normalising_constant; }
+uint64_t cb200_table_bytes(const cb200_decoder *d) { return d->table_bytes; }
+uint64_t cb200_graph_half_edges(const cb200_decoder *d) { return d->host.adj.size(); }
+
+char *cb200_describe(const cb200_decoder *d) {
+    std::string s = d->host.describe();
+    char *r = (char *)malloc(s.size() + 1);
+    if (r) memcpy(r, s.c_str(), s.size() + 1);
+    return r;
+}
+void cb200_free_string(char *s) { free(s); }
+
+int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2) {
+    if (group_threads != 0 && group_threads != 1 && group_threads != 32 && group_threads != 128) {
+        g_error = "group_threads must be 0, 1, 32 or 128";
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+    if (ht_log2 != 0 && (ht_log2 < 4 || ht_log2 > 24)) {
+        g_error = "ht_log2 must be 0 or within [4, 24]";
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+    d->tune_group = group_threads;
+    d->tune_ht_log2 = ht_log2;
+    return CB200_OK;
+}
+
+int cb200_decode_batch(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
+                       float *weight_out, int64_t *weight_int_out, uint32_t flags, cb200_batch_stats *stats) {
+    return guarded([&]() {
+        if (!d) throw std::invalid_argument("decoder must not be null");
+        if (num_shots && !dets && cb200_num_detector_bytes(d)) throw std::invalid_argument("dets must not be null");
+        if (num_shots && !obs_out && cb200_num_observable_bytes(d)) throw std::invalid_argument("obs_out must not be null");
+        return decode_impl(d, dets, num_shots, row_stride, obs_out, weight_out, weight_int_out, flags, stats, nullptr, 0,
+                           nullptr, nullptr);
+    });
+}
+
+int cb200_decode_shot_edges(cb200_decoder *d, const uint8_t *dets_row, int64_t *edges_out, uint64_t edges_cap,
+                            uint64_t *num_edge_ints, uint64_t *obs_mask_out, int64_t *weight_int_out) {
+    return guarded([&]() {
+        if (!d || !dets_row) throw std::invalid_argument("decoder and dets_row must not be null");
+        std::vector<uint8_t> obs(std::max<uint64_t>(cb200_num_observable_bytes(d), 1));
+        uint64_t need = 0;
+        int rc = decode_impl(d, dets_row, 1, cb200_num_detector_bytes(d), obs.data(), nullptr, weight_int_out, CB200_IO_HOST,
+                             nullptr, edges_out, edges_cap, &need, obs_mask_out);
+        if (num_edge_ints) *num_edge_ints = need;
+        return rc;
+    });
+}
+
+}  // extern "C"

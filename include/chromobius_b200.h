@@ -1,0 +1,110 @@
+/* chromobius_b200.h -- C ABI of the B200 batched colour-code decoder.
+ *
+ * This is the drop-in boundary for ONE path of quantumlib/chromobius: the per-shot decode loop behind
+ * `CompiledDecoder.predict_obs_flips_from_dets_bit_packed`. The reference has no FFI of its own; its boundary is the
+ * C++ `chromobius::Decoder` behind pybind11. Every entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/src/chromobius). A binding that keeps the reference's Python surface on top of
+ * this ABI is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, no global state besides a thread-local error string.
+ * Every function that can fail returns 0 on success and a negative CB200_ERR_* code otherwise;
+ * cb200_last_error() then describes the failure (the reference throws std::invalid_argument with that text).
+ * A decoder handle owns device memory on one GPU and must not be used from two threads at once
+ * (same rule as the reference's Decoder, decode/decoder.h:64-144).
+ */
+#ifndef CHROMOBIUS_B200_H
+#define CHROMOBIUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_OK 0
+#define CB200_ERR_INVALID_ARGUMENT (-1) /* what the reference reports as std::invalid_argument */
+#define CB200_ERR_CUDA (-2)             /* CUDA runtime failure (no GPU, out of memory, launch error) */
+#define CB200_ERR_DECODE (-3)           /* a shot could not be decoded; see cb200_batch_stats.first_failed_shot */
+
+/* cb200_decode_batch flags */
+#define CB200_IO_HOST 0u   /* dets / outputs are host pointers; copies are part of the call */
+#define CB200_IO_DEVICE 1u /* dets / outputs are device pointers on the decoder's GPU */
+
+typedef struct cb200_decoder cb200_decoder;
+
+typedef struct cb200_batch_stats {
+    uint64_t num_shots;
+    uint64_t num_detection_events; /* after masking ignored detectors and pad bits */
+    uint64_t num_retried_shots;    /* shots re-run with enlarged scratch */
+    uint64_t num_failed_shots;
+    int64_t first_failed_shot;     /* -1 if none */
+    uint32_t first_failed_status;  /* cb200 ShotStatus of that shot */
+    uint32_t max_events_per_shot;
+    uint32_t group_threads;        /* threads cooperating on one shot in the matcher kernel (32 = warp, else block) */
+    uint32_t num_groups;
+    uint64_t kernel_launches;      /* kernels launched by this call */
+    float ms_h2d, ms_count, ms_decode, ms_d2h, ms_total; /* CUDA-event times on the decoder's stream */
+    uint64_t matcher_rounds;       /* sum over shots of certified-matching rounds */
+} cb200_batch_stats;
+
+/* Thread-local description of the most recent failure in this thread. */
+const char *cb200_last_error(void);
+
+/* Compile a decoder from detector-error-model text and upload its tables to `device`.
+ * Replaces Decoder::from_dem (decode/decoder.cc:24-69) as reached from CompiledDecoder::from_dem
+ * (pybind/chromobius.pybind.cc:32-47), which also hands the DEM over as text. */
+int cb200_compile(const char *dem_text, int device, cb200_decoder **out);
+
+/* Releases host and device memory. */
+void cb200_free(cb200_decoder *dec);
+
+/* Decoder::node_colors.size() / num_observables, as exposed through pybind/chromobius.pybind.cc:40-46. */
+uint64_t cb200_num_detectors(const cb200_decoder *dec);
+uint64_t cb200_num_observables(const cb200_decoder *dec);
+uint64_t cb200_num_detector_bytes(const cb200_decoder *dec);   /* ceil(num_detectors / 8) */
+uint64_t cb200_num_observable_bytes(const cb200_decoder *dec); /* ceil(num_observables / 8) */
+/* PymatchingMatcher::weight_scale = flooder.graph.normalising_constant (decode/pymatcher.cc:23). */
+double cb200_normalising_constant(const cb200_decoder *dec);
+
+/* Text dump of the compiled tables in the layout of Decoder's operator<< (decode/decoder.cc:279-291),
+ * i.e. what `chromobius describe_decoder` prints. Returns a malloc'd string; free with cb200_free_string. */
+char *cb200_describe(const cb200_decoder *dec);
+void cb200_free_string(char *s);
+
+/* Decode a batch of bit-packed shots.
+ * Replaces the serial loop over Decoder::decode_detection_events (decode/decoder.cc:249-277) in
+ * CompiledDecoder::predict_obs_flips_from_dets_bit_packed (pybind/chromobius.pybind.cc:49-117) and in
+ * ChromobiusSinterCompiledDecoder::decode_shots_bit_packed (pybind/sinter_compat.pybind.cc:30-72).
+ *
+ *   dets            num_shots rows of cb200_num_detector_bytes() bytes, `row_stride` bytes apart
+ *                   (bit d of a shot = (row[d >> 3] >> (d & 7)) & 1). Pad bits and ignored detectors are masked.
+ *   obs_out         num_shots x cb200_num_observable_bytes() bytes, little-endian observable mask per shot
+ *   weight_out      nullable; float32 per shot = integer matching weight / normalising constant
+ *                   (PymatchingMatcher::match_edges, decode/pymatcher.cc:32-41)
+ *   weight_int_out  nullable; int64 per shot, the exact integer matching weight (parity hook)
+ *   flags           CB200_IO_HOST or CB200_IO_DEVICE
+ *   stats           nullable
+ * A shot that cannot be decoded fails the whole call with CB200_ERR_DECODE, as the reference's exception does. */
+int cb200_decode_batch(cb200_decoder *dec, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
+                       float *weight_out, int64_t *weight_int_out, uint32_t flags, cb200_batch_stats *stats);
+
+/* Decode one host shot and also return the matched graph edges (the MatcherInterface::match_edges contract,
+ * decode/matcher_interface.h:29-45: interleaved node pairs of the Moebius graph). Test / debugging hook.
+ * `*num_edge_ints` receives the number of int64 values the full list needs (may exceed edges_cap). */
+int cb200_decode_shot_edges(cb200_decoder *dec, const uint8_t *dets_row, int64_t *edges_out, uint64_t edges_cap,
+                            uint64_t *num_edge_ints, uint64_t *obs_mask_out, int64_t *weight_int_out);
+
+/* Tuning knobs (0 keeps the automatic choice): threads per shot in the matcher kernel (1, 32 or 128) and the
+ * initial log2 size of the per-thread Dijkstra table. */
+int cb200_set_tuning(cb200_decoder *dec, uint32_t group_threads, uint32_t ht_log2);
+
+/* Sizes of the device-resident tables, for DESIGN.md / bench reporting. */
+uint64_t cb200_table_bytes(const cb200_decoder *dec);
+uint64_t cb200_graph_half_edges(const cb200_decoder *dec);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -37,6 +37,24 @@ void *cbsim_compile(const char *dem_text) {
 void cbsim_free(void *h) { delete (Sim *)h; }
 uint64_t cbsim_num_detectors(void *h) { return ((Sim *)h)->tables.num_dets; }
 uint64_t cbsim_num_observables(void *h) { return ((Sim *)h)->tables.num_obs; }
+double cbsim_normalising_constant(void *h) { return ((Sim *)h)->tables.normalising_constant; }
+static char *dup_string(const std::string &s) {
+    char *r = (char *)malloc(s.size() + 1);
+    memcpy(r, s.c_str(), s.size() + 1);
+    return r;
+}
+char *cbsim_describe(void *h) { return dup_string(((Sim *)h)->tables.describe()); }
+char *cbsim_mobius_dem(void *h) { return dup_string(((Sim *)h)->tables.mobius_dem_text()); }
+void cbsim_free_string(char *s) { free(s); }
+uint64_t cbsim_graph_half_edges(void *h) { return ((Sim *)h)->tables.adj.size(); }
+void cbsim_graph_export(void *h, uint32_t *row_ptr, uint32_t *nbr, int32_t *wt) {
+    auto &t = ((Sim *)h)->tables;
+    memcpy(row_ptr, t.row_ptr.data(), t.row_ptr.size() * 4);
+    for (size_t k = 0; k < t.adj.size(); k++) {
+        nbr[k] = t.adj[k].nbr;
+        wt[k] = t.adj[k].wt;
+    }
+}
 
 // Decodes shots one by one. Returns 0. status_out[k] != 0 marks failed shots.
 // edges_out (nullable): matched edges of the LAST shot (interleaved), *num_edge_ints receives the count.

@@ -1,0 +1,73 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded shots."""
+import numpy as np
+import pytest
+
+from dem_util import read_dem, NumpyDemSampler
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (dem, shots, seed)
+    ('phenom_color_code_d5_r5_p1000', 20000, 0),
+    ('phenom_color_code_d5_r5_p1000_with_ignored', 4000, 1),
+    ('midout_color_code_d5_r10_p1000', 4000, 0),
+    ('superdense_color_code_d5_r20_p1000', 2000, 0),
+    ('color2surface_d7_phenom_r7_p100', 2000, 0),
+    ('color2surface_d5_transit_p100', 2000, 0),
+    ('surface_code_d5_r5_p1000', 3000, 0),
+    ('rep_code_rg_d9_transit_p10', 3000, 0),
+    ('midout_color_code_d9_r36_p1000', 600, 0),
+    ('midout488_color_code_d9_r33_p1000', 600, 0),
+]
+
+
+def masks(pred):
+    out = np.zeros(pred.shape[0], np.uint64)
+    for k in range(pred.shape[1]):
+        out |= pred[:, k].astype(np.uint64) << np.uint64(8 * k)
+    return out
+
+
+@pytest.fixture(scope='module')
+def libs(built):
+    import chromobius_b200
+    import oracle
+    chromobius_b200.load_library()
+    return chromobius_b200, oracle
+
+
+@pytest.mark.parametrize('group', [32, 128, 1])
+@pytest.mark.parametrize('name,shots,seed', CASES)
+def test_batch_matches_oracle(libs, name, shots, seed, group):
+    cb, oracle = libs
+    text = read_dem(name)
+    dec = cb._compile_text(text, device=0)
+    dec.set_tuning(group_threads=group)
+    if group == 1:
+        shots = min(shots, 1000)
+    dets, _ = NumpyDemSampler(text).sample(shots, seed)
+    pred, wint = dec.decode_with_integer_weights(dets)
+    o_obs, o_w = oracle.OracleDecoder(text).decode_batch(dets)
+    assert dec.last_stats.group_threads == group
+    assert (wint == o_w).all(), 'integer matching weights must be bit exact on every shot'
+    diff = int((masks(pred) != o_obs).sum())
+    # Equal-weight matchings may legitimately lift to different predictions; they are counted, not hidden.
+    assert diff <= max(2, shots // 200), 'tie-break divergences: %d of %d' % (diff, shots)
+
+
+@pytest.mark.parametrize('name', ['midout_color_code_d5_r10_p1000', 'superdense_color_code_d5_r20_p1000'])
+def test_lift_of_gpu_edges_matches_oracle_lift(libs, name):
+    """Stages 3-4 in isolation: the oracle's Euler tour + discharge on the GPU's own matched edges gives the GPU's answer."""
+    cb, oracle = libs
+    text = read_dem(name)
+    dec = cb._compile_text(text, device=0)
+    od = oracle.OracleDecoder(text)
+    dets, _ = NumpyDemSampler(text).sample(200, 3)
+    for row in dets[:60]:
+        edges, obs, w = dec.decode_shot_edges(row)
+        if len(edges) == 0:
+            assert obs == 0 and w == 0
+            continue
+        assert od.lift_edges(row, edges) == obs
+        _, o_obs, o_w = od.decode_edges(row)
+        assert o_w == w

@@ -1,0 +1,41 @@
+"""Quick GPU probe: decode sampled shots of one DEM with each group width; print timing + parity vs oracle (optional)."""
+import sys, os, time
+import numpy as np
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import chromobius_b200 as cb
+from dem_util import read_dem
+from synth import FastDemSampler
+
+name = sys.argv[1]; shots = int(sys.argv[2]); groups = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [32, 128]
+check = len(sys.argv) > 4 and sys.argv[4] == 'check'
+text = read_dem(name)
+t0 = time.time(); dec = cb._compile_text(text, device=0); t1 = time.time()
+smp = FastDemSampler(text)
+dets, obs = smp.sample(shots, 0)
+t2 = time.time()
+print('%s: compile %.2fs sample %.2fs D=%d table_bytes=%d' % (name, t1 - t0, t2 - t1, dec.num_detectors, dec.table_bytes), flush=True)
+ref = None
+for g in groups:
+    dec.set_tuning(group_threads=g)
+    for rep in range(2):
+        t0 = time.time()
+        pred, wint = dec.decode_with_integer_weights(dets)
+        dt = time.time() - t0
+        st = dec.last_stats
+        print('  group=%3d rep%d wall %.3fs  decode %.2f ms (%.2f us/shot, %.0f shots/s) count %.3f ms h2d %.2f ms events/shot %.1f rounds/shot %.2f retried %d groups %d' % (
+            g, rep, dt, st.ms_decode, st.ms_decode * 1e3 / shots, shots / (st.ms_decode * 1e-3), st.ms_count, st.ms_h2d,
+            st.num_detection_events / shots, st.matcher_rounds / shots, st.num_retried_shots, st.num_groups), flush=True)
+    if ref is None:
+        ref = (pred.copy(), wint.copy())
+    else:
+        print('  vs first group: weight diffs %d obs diffs %d' % ((wint != ref[1]).sum(), (pred != ref[0]).any(axis=1).sum()))
+m = np.zeros(shots, np.uint64)
+for k in range(ref[0].shape[1]):
+    m |= ref[0][:, k].astype(np.uint64) << np.uint64(8 * k)
+print('  mistakes %d / %d' % ((m != obs).sum(), shots))
+if check:
+    import oracle
+    n = min(shots, int(sys.argv[5]) if len(sys.argv) > 5 else 500)
+    oo, ow = oracle.OracleDecoder(text).decode_batch(dets[:n])
+    print('  oracle check on %d shots: weight diffs %d obs diffs %d' % (n, (ow != ref[1][:n]).sum(), (oo != m[:n]).sum()))
