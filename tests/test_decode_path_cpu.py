@@ -1,0 +1,154 @@
+"""CPU tier: the device decode logic (host simulation build, group of one thread) against the oracle, the oracle's
+matcher against brute force, and the RNG-free single-error property of the reference's integration test."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from dem_util import read_dem, NumpyDemSampler
+from sim_util import SimDecoder
+
+SMALL = [
+    ('phenom_color_code_d5_r5_p1000', 6000),
+    ('phenom_color_code_d5_r5_p1000_with_ignored', 3000),
+    ('midout_color_code_d5_r10_p1000', 1500),
+    ('superdense_color_code_d5_r20_p1000', 400),
+    ('color2surface_d7_phenom_r7_p100', 300),
+    ('color2surface_d5_transit_p100', 1500),
+    ('surface_code_d5_r5_p1000', 1500),
+    ('rep_code_d9_transit_p10', 1500),
+    ('rep_code_rg_d9_transit_p10', 1500),
+    ('rep_code_rbrrr_d9_transit_p10', 1500),
+]
+
+
+@pytest.mark.parametrize('name,shots', SMALL)
+def test_device_logic_matches_oracle(built, name, shots):
+    text = read_dem(name)
+    dets, _ = NumpyDemSampler(text).sample(shots, seed=11)
+    sim = SimDecoder(text)
+    obs, w, st, rd = sim.decode(dets)
+    o_obs, o_w = oracle.OracleDecoder(text).decode_batch(dets)
+    assert (st == 0).all()
+    assert (w == o_w).all(), 'integer matching weights must be bit exact'
+    assert int((obs != o_obs).sum()) <= max(1, shots // 300)
+
+
+def test_device_logic_survives_tiny_scratch(built):
+    """Scratch overflow is reported per shot (status 1), never silently wrong."""
+    text = read_dem('midout_color_code_d5_r10_p1000')
+    dets, _ = NumpyDemSampler(text).sample(300, seed=2)
+    sim = SimDecoder(text)
+    good = sim.decode(dets)
+    obs, w, st, rd = sim.decode(dets, ht_log2=4, dyn_bytes=4096)
+    assert set(np.unique(st)) <= {0, 1}
+    ok = st == 0
+    assert (obs[ok] == good[0][ok]).all() and (w[ok] == good[1][ok]).all()
+    assert (st == 1).any()
+
+
+def all_pairs_dist(row_ptr, nbr, wt, sources):
+    import heapq
+    out = {}
+    for s in sources:
+        dist = {s: 0}
+        pq = [(0, s)]
+        while pq:
+            d, u = heapq.heappop(pq)
+            if d != dist[u]:
+                continue
+            for k in range(row_ptr[u], row_ptr[u + 1]):
+                v = int(nbr[k])
+                nd = d + int(wt[k])
+                if v not in dist or nd < dist[v]:
+                    dist[v] = nd
+                    heapq.heappush(pq, (nd, v))
+        out[s] = dist
+    return out
+
+
+def brute_force_mwpm(events, dist):
+    best = [None]
+
+    def rec(rest, acc):
+        if best[0] is not None and acc >= best[0]:
+            return
+        if not rest:
+            best[0] = acc
+            return
+        a = rest[0]
+        for k in range(1, len(rest)):
+            b = rest[k]
+            d = dist[a].get(b)
+            if d is None:
+                continue
+            rec(rest[1:k] + rest[k + 1:], acc + d)
+
+    rec(list(events), 0)
+    return best[0]
+
+
+@pytest.mark.parametrize('name', ['midout_color_code_d5_r10_p1000', 'color2surface_d5_transit_p100', 'surface_code_d5_r5_p1000'])
+def test_matching_weight_against_brute_force(built, name):
+    """Exhaustive pairing over exact all-pairs distances pins the integer weight for shots with <= 10 matcher events."""
+    text = read_dem(name)
+    od = oracle.OracleDecoder(text)
+    sim = SimDecoder(text)
+    row_ptr, nbr, wt = od.graph()
+    r2, n2, w2 = sim.graph()
+    assert (row_ptr == r2).all() and (nbr == n2).all() and (wt == w2).all(), 'oracle and product build the same matcher graph'
+    smp = NumpyDemSampler(text)
+    dets, _ = smp.sample(3000, seed=7)
+    nc = od.node_colors()
+    checked = 0
+    for row in dets:
+        bits = np.unpackbits(row, bitorder='little')[:od.num_detectors]
+        ds = [d for d in np.nonzero(bits)[0] if not nc[d, 2]]
+        if not (2 <= len(ds) <= 5):
+            continue
+        events = [2 * int(d) + s for d in ds for s in (0, 1)]
+        dist = all_pairs_dist(row_ptr, nbr, wt, events)
+        want = brute_force_mwpm(events, dist)
+        got_o = od.decode_batch(row[None, :])[1][0]
+        got_s = sim.decode(row[None, :])[1][0]
+        assert want == got_o == got_s
+        checked += 1
+        if checked >= 120:
+            break
+    assert checked >= 20
+
+
+@pytest.mark.parametrize('name', [n for n, _ in SMALL] + ['midout_color_code_d9_r36_p1000'])
+def test_single_error_resilience(built, name):
+    """decode/decoder_integration.test.cc:44-120: forcing exactly DEM error k (k < num_detectors, as in the reference's
+    loop bound) must be decoded to that error's observable mask. RNG-free known-answer test."""
+    text = read_dem(name)
+    smp = NumpyDemSampler(text)
+    n = min(smp.num_dets, len(smp.p))
+    if name.startswith('midout_color_code_d9'):
+        ks = list(range(0, n, 7))
+    else:
+        ks = list(range(n))
+    rows = np.zeros((len(ks), smp.nbytes), np.uint8)
+    want = np.zeros(len(ks), np.uint64)
+    for i, k in enumerate(ks):
+        rows[i], want[i] = smp.single_error_shot(k)
+    sim = SimDecoder(text)
+    obs, w, st, rd = sim.decode(rows)
+    assert (st == 0).all()
+    assert (obs == want).all()
+    o_obs, _ = oracle.OracleDecoder(text).decode_batch(rows)
+    assert (o_obs == want).all()
+
+
+def test_lift_is_pinned_on_oracle_edges(built):
+    """Stages 3-4 of the device logic, fed the device's own matched edges, agree with the oracle's Euler tour + discharge."""
+    text = read_dem('superdense_color_code_d5_r20_p1000')
+    od = oracle.OracleDecoder(text)
+    sim = SimDecoder(text)
+    dets, _ = NumpyDemSampler(text).sample(120, seed=4)
+    for row in dets:
+        obs, w, st, rd, edges = sim.decode(row, want_edges=True)
+        if len(edges):
+            assert od.lift_edges(row, edges) == int(obs[0])
