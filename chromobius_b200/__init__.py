@@ -94,6 +94,21 @@ def load_library():
     L.cb200_decode_shot_edges.argtypes = [vp, vp, vp, u64, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(i64)]
     L.cb200_set_tuning.restype = ctypes.c_int
     L.cb200_set_tuning.argtypes = [vp, u32, u32]
+    L.cb200_profile_phases.restype = ctypes.c_int
+    L.cb200_profile_phases.argtypes = [vp, ctypes.c_int, vp]
+    L.cb200_sampler_last_error.restype = ctypes.c_char_p
+    L.cb200_sampler_create.restype = ctypes.c_int
+    L.cb200_sampler_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
+    L.cb200_sampler_free.argtypes = [vp]
+    L.cb200_sampler_free.restype = None
+    L.cb200_sampler_num_detectors.restype = u64
+    L.cb200_sampler_num_detectors.argtypes = [vp]
+    L.cb200_sampler_num_observables.restype = u64
+    L.cb200_sampler_num_observables.argtypes = [vp]
+    L.cb200_sampler_expected_events_per_shot.restype = ctypes.c_double
+    L.cb200_sampler_expected_events_per_shot.argtypes = [vp]
+    L.cb200_sampler_sample.restype = ctypes.c_int
+    L.cb200_sampler_sample.argtypes = [vp, u64, u64, u64, vp, u64, vp, u32]
     _lib = L
     return L
 
@@ -251,6 +266,13 @@ class CompiledDecoder:
         if self._L.cb200_set_tuning(self._h, group_threads, ht_log2) != 0:
             _raise_last(self._L)
 
+    def profile_phases(self, enable=True):
+        """Enables phase profiling for later calls; returns the cycle counters of the last profiled call as a dict."""
+        buf = (ctypes.c_ulonglong * 8)()
+        self._L.cb200_profile_phases(self._h, 1 if enable else 0, buf)
+        names = ['ingest', 'explore_first', 'components', 'solve', 'explore_regrow', 'paths', 'lift', 'shots']
+        return dict(zip(names, [int(x) for x in buf]))
+
     def describe(self):
         p = self._L.cb200_describe(self._h)
         try:
@@ -359,3 +381,45 @@ class _ChromobiusSinterDecoder:
 def sinter_decoders():
     """A dictionary describing chromobius to sinter (pybind/sinter_compat.pybind.cc:224-241)."""
     return {'chromobius': _ChromobiusSinterDecoder(0)}
+
+
+class DeviceDemSampler:
+    """On-device DEM sampler (the stim::DemSampler role in front of the decode path; include/chromobius_b200.h)."""
+
+    def __init__(self, dem_text, device=None):
+        L = load_library()
+        h = ctypes.c_void_p()
+        rc = L.cb200_sampler_create(str(dem_text).encode(), _default_device() if device is None else int(device), ctypes.byref(h))
+        if rc != 0:
+            msg = L.cb200_sampler_last_error().decode('utf-8', 'replace')
+            raise (RuntimeError if rc == -2 else ValueError)(msg)
+        self._h, self._L = h, L
+        self.num_detectors = int(L.cb200_sampler_num_detectors(h))
+        self.num_observables = int(L.cb200_sampler_num_observables(h))
+        self.num_detector_bytes = (self.num_detectors + 7) // 8
+        self.expected_events_per_shot = float(L.cb200_sampler_expected_events_per_shot(h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.cb200_sampler_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def sample(self, num_shots, seed=0, first_shot=0):
+        """-> (dets uint8[num_shots, num_detector_bytes], obs uint64[num_shots]) on the host."""
+        dets = np.zeros((num_shots, self.num_detector_bytes), np.uint8)
+        obs = np.zeros(num_shots, np.uint64)
+        rc = self._L.cb200_sampler_sample(self._h, num_shots, seed, first_shot, dets.ctypes.data_as(ctypes.c_void_p),
+                                          self.num_detector_bytes, obs.ctypes.data_as(ctypes.c_void_p), CB200_IO_HOST)
+        if rc != 0:
+            raise RuntimeError(self._L.cb200_sampler_last_error().decode('utf-8', 'replace'))
+        return dets, obs
+
+    def sample_device(self, num_shots, dets_ptr, row_stride, obs_ptr=None, seed=0, first_shot=0):
+        """Writes shots straight into device memory (addresses as integers)."""
+        rc = self._L.cb200_sampler_sample(self._h, num_shots, seed, first_shot, ctypes.c_void_p(dets_ptr), row_stride,
+                                          ctypes.c_void_p(obs_ptr) if obs_ptr else None, CB200_IO_DEVICE)
+        if rc != 0:
+            raise RuntimeError(self._L.cb200_sampler_last_error().decode('utf-8', 'replace'))

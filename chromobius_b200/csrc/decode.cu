@@ -195,6 +195,9 @@ struct cb200_decoder {
     DeviceBuf<uint64_t> d_obs64;
     DeviceBuf<int64_t> d_wint, d_wint_out, d_edges;
     DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list;
+    DeviceBuf<unsigned long long> d_phase;
+    bool profile_phases = false;
+    unsigned long long phase_cycles[8] = {};
     DeviceBuf<float> d_wfloat;
     // arena layout currently initialised on the device
     ScratchConfig arena_cfg{};
@@ -379,6 +382,11 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     p.status_out = d->d_status.ptr;
     p.rounds_out = d->d_rounds.ptr;
     p.work_counter = d->d_scalars.ptr + 4;
+    if (d->profile_phases) {
+        d->d_phase.ensure(8);
+        CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 64, s));
+        p.phase_cycles = d->d_phase.ptr;
+    }
     if (edges_out || num_edge_ints) {
         d->d_edges.ensure(edges_cap + 2);
         p.edge_dump = d->d_edges.ptr;
@@ -465,6 +473,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         CUDA_CHECK(cudaStreamSynchronize(s));
         for (uint32_t r : rounds) st.matcher_rounds += r;
     }
+    if (d->profile_phases) CUDA_CHECK(cudaMemcpyAsync(d->phase_cycles, d->d_phase.ptr, 64, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaEventRecord(d->ev[5], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     st.kernel_launches = launches;
@@ -546,7 +555,7 @@ void cb200_free(cb200_decoder *d) {
     d->d_det_info.release(); d->d_ingest_mask.release(); d->d_rep_obs.release(); d->d_drag.release();
     d->d_dets.release(); d->d_obs_bytes.release(); d->d_arena.release(); d->d_obs64.release(); d->d_wint.release();
     d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();
-    d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release();
+    d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release(); d->d_phase.release();
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -580,6 +589,13 @@ int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2)
     }
     d->tune_group = group_threads;
     d->tune_ht_log2 = ht_log2;
+    return CB200_OK;
+}
+
+int cb200_profile_phases(cb200_decoder *d, int enable, unsigned long long *cycles_out8) {
+    if (!d) return CB200_ERR_INVALID_ARGUMENT;
+    if (cycles_out8) memcpy(cycles_out8, d->phase_cycles, sizeof(d->phase_cycles));
+    d->profile_phases = enable != 0;
     return CB200_OK;
 }
 

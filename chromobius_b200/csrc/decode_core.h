@@ -92,6 +92,10 @@ struct DecodeParams {
     uint64_t arena_stride;
     ScratchConfig cfg;
     uint32_t *work_counter;      // persistent-kernel shot queue
+    // optional profiling: cycles spent by thread 0 of every group in
+    // [0] ingest [1] first exploration [2] component building [3] component solves [4] re-exploration
+    // [5] path extraction [6] Euler tours + discharge [7] shots
+    unsigned long long *phase_cycles;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -108,6 +112,26 @@ CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { uint64_t o = *p; *p = 
 CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { uint32_t o = *p; if (o == expect) *p = v; return o; }
 CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 #endif
+
+#ifdef __CUDA_ARCH__
+CB_HD unsigned long long cb_clock() { return (unsigned long long)clock64(); }
+#else
+CB_HD unsigned long long cb_clock() { return 0; }
+#endif
+
+struct PhaseTimer {
+    unsigned long long t[8];
+    unsigned long long last;
+    CB_HD void start() {
+        for (int k = 0; k < 8; k++) t[k] = 0;
+        last = cb_clock();
+    }
+    CB_HD void lap(int phase) {
+        unsigned long long now = cb_clock();
+        t[phase] += now - last;
+        last = now;
+    }
+};
 
 struct HostGroup {
     int tid = 0;
@@ -970,7 +994,7 @@ CB_HD void solve_component(Shot &s, uint32_t c) {
 }
 
 template <class G>
-CB_HD uint32_t match_shot(Shot &s, const G &g) {
+CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     const uint32_t M = s.M;
     for (uint32_t i = g.tid; i < M; i += g.n) {
         s.partner[i] = -1;
@@ -983,6 +1007,7 @@ CB_HD uint32_t match_shot(Shot &s, const G &g) {
     uint32_t round = 0;
     while (true) {
         g.sync();
+        pt.lap(round == 0 ? 1 : 4);
         if (s.hdr->status) return round;
         if (++round > MAX_ROUNDS) {
             if (g.tid == 0) s.fail(SHOT_ROUND_LIMIT);
@@ -1032,8 +1057,10 @@ CB_HD uint32_t match_shot(Shot &s, const G &g) {
         }
         g.sync();
         const uint32_t ncomp = s.hdr->ncomp;
+        pt.lap(2);
         for (uint32_t c = g.tid; c < ncomp; c += g.n) solve_component(s, c);
         g.sync();
+        pt.lap(3);
         const uint32_t st = s.hdr->status;
         const uint32_t ngrow = s.hdr->ngrow;
         g.sync();  // everyone has read the verdict before the next phase may change it
@@ -1387,17 +1414,26 @@ CB_HD bool lift_shot(Shot &s, uint64_t *obs_out, int64_t *edge_dump, uint64_t ed
 // One shot, start to finish. `shot` indexes the caller's arrays.
 template <class G>
 CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g) {
+    PhaseTimer pt;
+    pt.start();
     ingest_shot(s, p.dets + (uint64_t)shot * p.stride, g);
+    pt.lap(0);
     uint32_t rounds = 0;
     if (!s.hdr->status && s.M) {
-        rounds = match_shot(s, g);
+        rounds = match_shot(s, g, pt);
         if (!s.hdr->status) paths_shot(s, g);
     }
     g.sync();
+    pt.lap(5);
     if (g.tid == 0) {
         uint64_t obs = 0;
         if (!s.hdr->status && s.M) lift_shot(s, &obs, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
         else if (p.edge_dump_len) *p.edge_dump_len = 0;
+        pt.lap(6);
+        if (p.phase_cycles) {
+            for (int k = 0; k < 7; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[k], pt.t[k]);
+            cb_atomic_add64((uint64_t *)&p.phase_cycles[7], 1);
+        }
         uint32_t st = s.hdr->status;
         p.status_out[shot] = st;
         p.obs_out[shot] = st ? 0 : obs;

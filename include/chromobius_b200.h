@@ -99,9 +99,32 @@ int cb200_decode_shot_edges(cb200_decoder *dec, const uint8_t *dets_row, int64_t
  * initial log2 size of the per-thread Dijkstra table. */
 int cb200_set_tuning(cb200_decoder *dec, uint32_t group_threads, uint32_t ht_log2);
 
+/* Phase profiling of the decode kernel (clock64 of thread 0 of every group, summed over shots). Enables/disables it
+ * for later calls and copies out the counters of the most recent profiled call:
+ * [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
+ * [5] path extraction [6] Euler tours + discharge [7] number of shots. */
+int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cycles_out8);
+
 /* Sizes of the device-resident tables, for DESIGN.md / bench reporting. */
 uint64_t cb200_table_bytes(const cb200_decoder *dec);
 uint64_t cb200_graph_half_edges(const cb200_decoder *dec);
+
+/* ---- On-device syndrome sampler: the step in front of the decode path --------------
+ * Plays the role of stim::DemSampler in the reference's tests (decode/decoder_integration.test.cc:55-68): each error
+ * mechanism of the DEM fires independently with its probability, a shot is the XOR of the fired symptoms.
+ * Output layout equals the decoder's input layout, so sampled shots can be decoded without leaving HBM. */
+typedef struct cb200_sampler cb200_sampler;
+const char *cb200_sampler_last_error(void);
+int cb200_sampler_create(const char *dem_text, int device, cb200_sampler **out);
+void cb200_sampler_free(cb200_sampler *s);
+uint64_t cb200_sampler_num_detectors(const cb200_sampler *s);
+uint64_t cb200_sampler_num_observables(const cb200_sampler *s);
+double cb200_sampler_expected_events_per_shot(const cb200_sampler *s);
+/* Shots [first_shot, first_shot + num_shots) of the stream identified by `seed`.
+ * dets_out: num_shots rows, row_stride bytes apart; obs_out (nullable): one u64 observable mask per shot.
+ * flags: CB200_IO_HOST or CB200_IO_DEVICE for both outputs. */
+int cb200_sampler_sample(cb200_sampler *s, uint64_t num_shots, uint64_t seed, uint64_t first_shot, uint8_t *dets_out,
+                         uint64_t row_stride, uint64_t *obs_out, uint32_t flags);
 
 #ifdef __cplusplus
 }

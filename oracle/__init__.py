@@ -55,6 +55,7 @@ def lib():
         L.orc_euler_tours.argtypes = [u64, vp, u64, vp, u64]
         L.orc_lift_edges.restype = i64
         L.orc_lift_edges.argtypes = [vp, vp, vp, u64, vp]
+        L.orc_set_matcher_mode.argtypes = [vp, ctypes.c_int]
         L.orc_match_events.restype = i64
         L.orc_match_events.argtypes = [vp, vp, u64, vp, vp]
         _lib = L
@@ -80,6 +81,10 @@ class OracleDecoder:
         self.num_detector_bytes = (self.num_detectors + 7) // 8
         self.num_observable_bytes = (self.num_observables + 7) // 8
         self.normalising_constant = L.orc_normalising_constant(self._h)
+
+    def set_matcher_mode(self, mode):
+        """0: dense all-pairs matcher up to 160 events, certified-local beyond; 1: always local; 2: always dense."""
+        lib().orc_set_matcher_mode(self._h, int(mode))
 
     def clone(self):
         return OracleDecoder(None, _handle=lib().orc_clone(self._h))

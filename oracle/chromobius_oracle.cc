@@ -534,6 +534,10 @@ struct Tables {
     std::vector<RgbRep> rgb_reps;
     std::vector<std::map<node_t, obsmask>> charge_graph;  // neighbor -> obs flip (BOUNDARY key allowed)
     std::map<std::array<uint32_t, 4>, obsmask> drag;      // {n1, n2, c1, c2}
+    std::unordered_map<uint64_t, obsmask> drag_lookup;    // same content, hashed (filled after the map is complete)
+    static uint64_t drag_key(uint32_t n1, uint32_t n2, uint32_t c1, uint32_t c2) {
+        return ((uint64_t)n1 << 34) | ((uint64_t)n2 << 4) | (c1 << 2) | c2;
+    }
     uint64_t drag_ambiguities = 0;
     // matcher graph (CSR over 2*num_dets nodes)
     std::vector<uint32_t> row_ptr, nbr;
@@ -808,6 +812,8 @@ static std::unique_ptr<Tables> compile(const std::string &dem_text) {
     t->rgb_reps = choose_rgb_reps(t->atomic_errors, nc);
     t->charge_graph = build_charge_graph(t->atomic_errors, nc.size());
     build_drag_graph(*t);
+    t->drag_lookup.reserve(t->drag.size() * 2);
+    for (const auto &kv : t->drag) t->drag_lookup[Tables::drag_key(kv.first[0], kv.first[1], kv.first[2], kv.first[3])] = kv.second;
     build_matcher_graph(*t);
     return t;
 }
@@ -834,10 +840,12 @@ struct DenseBlossom {
 
     void init(int n_) {
         n = n_;
-        int m = 2 * n + 2;
-        g.assign(m, std::vector<E>(m));
-        for (int u = 0; u < m; u++)
+        int m = n + n / 2 + 3;  // at most (n - 1) / 2 blossoms are alive at once
+        if ((int)g.size() < m) g.resize(m);
+        for (int u = 0; u < m; u++) {
+            if ((int)g[u].size() < m) g[u].resize(m);
             for (int v = 0; v < m; v++) g[u][v] = E{u, v, 0};
+        }
         lab.assign(m, 0);
         match.assign(m, 0);
         slack.assign(m, 0);
@@ -845,8 +853,10 @@ struct DenseBlossom {
         pa.assign(m, 0);
         S.assign(m, 0);
         vis.assign(m, 0);
-        flower_from.assign(m, std::vector<int>(n + 1, 0));
-        flower.assign(m, {});
+        if ((int)flower_from.size() < m) flower_from.resize(m);
+        for (int u = 0; u < m; u++) flower_from[u].assign(n + 1, 0);
+        if ((int)flower.size() < m) flower.resize(m);
+        for (int u = 0; u < m; u++) flower[u].clear();
     }
     void add_edge(int u, int v, int64_t w) {
         g[u][v].w = g[v][u].w = w;
@@ -1065,8 +1075,26 @@ struct MatchResult {
     int64_t weight = 0;
 };
 
+// std::priority_queue semantics (min-heap) over storage that survives between calls.
+struct ReusableHeap {
+    typedef std::pair<int64_t, node_t> QE;
+    std::vector<QE> v;
+    void clear() { v.clear(); }
+    bool empty() const { return v.empty(); }
+    const QE &top() const { return v.front(); }
+    void push(QE e) {
+        v.push_back(e);
+        std::push_heap(v.begin(), v.end(), std::greater<QE>());
+    }
+    void pop() {
+        std::pop_heap(v.begin(), v.end(), std::greater<QE>());
+        v.pop_back();
+    }
+};
+
 struct Decoder {
     std::unique_ptr<Tables> t;
+    ReusableHeap heap_buf;
     // scratch for dijkstra
     std::vector<int64_t> dist;
     std::vector<uint32_t> touched;
@@ -1081,6 +1109,10 @@ struct Decoder {
     std::string last_error;
     // statistics
     uint64_t stat_radius_retries = 0;
+    // 0 = dense all-pairs matcher up to 160 events, local beyond; 1 = always local; 2 = always dense
+    int matcher_mode = 0;
+    DenseBlossom local_blossom;
+    std::vector<int> loc_buf;
 
     explicit Decoder(std::unique_ptr<Tables> tt) : t(std::move(tt)) {
         size_t n = t->num_dets * 2;
@@ -1120,8 +1152,8 @@ struct Decoder {
     // Canonical shortest path src -> dst: full distances from src (bounded by d(src,dst)), then walk back from dst
     // always taking the smallest-id tight predecessor. Emits edges in walking order from src to dst.
     void canonical_path(node_t src, node_t dst, int64_t d_total, std::vector<int64_t> *out_edges) {
-        typedef std::pair<int64_t, node_t> QE;
-        std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+        ReusableHeap &pq = heap_buf;
+        pq.clear();
         touched.clear();
         dist[src] = 0;
         touched.push_back(src);
@@ -1170,6 +1202,20 @@ struct Decoder {
         out->weight = 0;
         int m = (int)events.size();
         if (m == 0) return true;
+        if (matcher_mode == 1 || (matcher_mode == 0 && m > 160)) {
+            std::vector<int> partner;
+            std::vector<int64_t> pdist;
+            if (!match_events_local(events, &partner, &pdist)) return false;
+            for (int i = 0; i < m; i++) {
+                int j = partner[i];
+                if (j > i) {
+                    out->weight += pdist[i];
+                    canonical_path((node_t)events[i], (node_t)events[j], pdist[i], &out->edges);
+                    if (out_pairs) out_pairs->push_back({i, j});
+                }
+            }
+            return true;
+        }
         for (int i = 0; i < m; i++) event_index[events[i]] = i;
         int64_t max_w = 0;
         for (auto w : t->wt) max_w = std::max<int64_t>(max_w, w);
@@ -1229,6 +1275,167 @@ struct Decoder {
             }
         }
         return true;
+    }
+
+    // Ball around one event (truncated Dijkstra). radius >= 0: everything within radius. radius < 0: until more than
+    // `need_more_than` other events are inside, then the whole distance level is finished. Returns the radius reached
+    // (-1 when nothing more is reachable).
+    int64_t ball(node_t src, int64_t radius, size_t need_more_than, std::vector<std::pair<int, int64_t>> *found) {
+        ReusableHeap &pq = heap_buf;
+        pq.clear();
+        touched.clear();
+        found->clear();
+        dist[src] = 0;
+        touched.push_back(src);
+        pq.push({0, src});
+        int64_t limit = radius;
+        while (!pq.empty()) {
+            auto [d, u] = pq.top();
+            pq.pop();
+            if (d != dist[u]) continue;
+            if (limit >= 0 && d > limit) break;
+            if (u != src && event_index[u] >= 0) {
+                found->push_back({event_index[u], d});
+                if (limit < 0 && found->size() > need_more_than) limit = d;
+            }
+            for (uint32_t k = t->row_ptr[u]; k < t->row_ptr[u + 1]; k++) {
+                node_t v = t->nbr[k];
+                int64_t nd = d + t->wt[k];
+                if (limit >= 0 && nd > limit) continue;
+                if (dist[v] < 0 || nd < dist[v]) {
+                    if (dist[v] < 0) touched.push_back(v);
+                    dist[v] = nd;
+                    pq.push({nd, v});
+                }
+            }
+        }
+        for (auto v : touched) dist[v] = -1;
+        return limit;
+    }
+
+    // Certified local matching: the same optimum as match_events_dense without the all-pairs step, usable at
+    // d25 r100 sizes. Balls grow until the blossom duals of every component fit inside them (2 y_a <= R_a), which keeps
+    // the duals feasible for every pair that was never looked at; see the argument in DESIGN.md ("Matcher").
+    bool match_events_local(const std::vector<uint64_t> &events, std::vector<int> *partner_out, std::vector<int64_t> *pdist_out) {
+        int m = (int)events.size();
+        partner_out->assign(m, -1);
+        pdist_out->assign(m, 0);
+        if (m == 0) return true;
+        for (int i = 0; i < m; i++) event_index[events[i]] = i;
+        std::vector<int64_t> R(m);
+        std::vector<std::vector<std::pair<int, int64_t>>> nb(m);
+        std::vector<char> dirty(m, 1);
+        bool ok = true;
+        for (int i = 0; i < m && ok; i++) {
+            R[i] = ball((node_t)events[i], -1, 0, &nb[i]);
+            if (R[i] < 0) ok = false;
+        }
+        std::vector<int> uf(m), comp_of(m);
+        std::vector<std::pair<int, int64_t>> grow;
+        for (int round = 0; ok; round++) {
+            if (round > 64) {
+                ok = false;
+                break;
+            }
+            for (int i = 0; i < m; i++) uf[i] = i;
+            auto find = [&](int x) {
+                while (uf[x] != x) {
+                    uf[x] = uf[uf[x]];
+                    x = uf[x];
+                }
+                return x;
+            };
+            for (int i = 0; i < m; i++)
+                for (auto &p : nb[i]) {
+                    int a = find(i), b = find(p.first);
+                    if (a != b) uf[std::max(a, b)] = std::min(a, b);
+                }
+            std::vector<std::pair<int, int>> by_root(m);
+            for (int i = 0; i < m; i++) by_root[i] = {find(i), i};
+            std::sort(by_root.begin(), by_root.end());
+            grow.clear();
+            std::vector<int> mem;
+            for (int a = 0; a < m;) {
+                int b = a;
+                mem.clear();
+                while (b < m && by_root[b].first == by_root[a].first) mem.push_back(by_root[b++].second);
+                a = b;
+                bool is_dirty = false;
+                for (int i : mem) is_dirty |= dirty[i] != 0;
+                if (!is_dirty) continue;
+                int n = (int)mem.size();
+                if (n % 2) {
+                    for (int i : mem) grow.push_back({i, -1});
+                    continue;
+                }
+                if (n == 2) {
+                    // one edge: the blossom sets y = d/2 on both ends, so both balls must reach d
+                    int i = mem[0], j = mem[1];
+                    int64_t d = -1;
+                    for (auto &p : nb[i])
+                        if (p.first == j) d = p.second;
+                    for (auto &p : nb[j])
+                        if (p.first == i) d = p.second;
+                    bool certified = true;
+                    for (int e : mem)
+                        if (d > R[e]) {
+                            grow.push_back({e, d});
+                            certified = false;
+                        }
+                    if (certified) {
+                        (*partner_out)[i] = j;
+                        (*partner_out)[j] = i;
+                        (*pdist_out)[i] = (*pdist_out)[j] = d;
+                    }
+                    continue;
+                }
+                std::vector<int> &loc = loc_buf;
+                loc.resize(m);
+                for (int k = 0; k < n; k++) loc[mem[k]] = k + 1;
+                int64_t big = 2;
+                for (int i : mem)
+                    for (auto &p : nb[i]) big = std::max(big, p.second + 2);
+                DenseBlossom &bl = local_blossom;
+                bl.init(n);
+                for (int i : mem)
+                    for (auto &p : nb[i]) bl.add_edge(loc[i], loc[p.first], big - p.second);
+                int cnt = bl.solve();
+                if (cnt * 2 != n) {
+                    for (int i : mem)
+                        if (!bl.match[loc[i]]) grow.push_back({i, -1});
+                    continue;
+                }
+                bool certified = true;
+                for (int i : mem) {
+                    int64_t need = big - bl.lab[loc[i]];
+                    if (need > R[i]) {
+                        grow.push_back({i, need});
+                        certified = false;
+                    }
+                }
+                if (certified)
+                    for (int i : mem) {
+                        int j = mem[bl.match[loc[i]] - 1];
+                        (*partner_out)[i] = j;
+                        for (auto &p : nb[i])
+                            if (p.first == j) (*pdist_out)[i] = (*pdist_out)[j] = p.second;
+                    }
+            }
+            std::fill(dirty.begin(), dirty.end(), 0);
+            if (grow.empty()) break;
+            for (auto &[i, to] : grow) {
+                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i]);
+                if (R[i] < 0) {
+                    ok = false;
+                    break;
+                }
+                dirty[i] = 1;
+                for (auto &p : nb[i]) dirty[p.first] = 1;
+            }
+        }
+        for (int i = 0; i < m; i++) event_index[events[i]] = -1;
+        if (!ok) last_error = "No perfect matching exists for the detection events.";
+        return ok;
     }
 
     // euler_tours.cc:21-32
@@ -1334,8 +1541,8 @@ struct Decoder {
                 for (uint32_t cc = 0; cc < 4; cc++) {
                     if (!cur[cc].has_value()) continue;
                     for (uint32_t ncg = 0; ncg < 4; ncg++) {
-                        auto f = t->drag.find({cur_loc, next_loc, cc, ncg});
-                        if (f != t->drag.end()) after[ncg] = *cur[cc] ^ f->second;
+                        auto f = t->drag_lookup.find(Tables::drag_key(cur_loc, next_loc, cc, ncg));
+                        if (f != t->drag_lookup.end()) after[ncg] = *cur[cc] ^ f->second;
                     }
                 }
                 cur = after;
@@ -1480,6 +1687,7 @@ uint64_t orc_num_observables(void *h) { return ((Decoder *)h)->t->num_obs; }
 double orc_normalising_constant(void *h) { return ((Decoder *)h)->t->normalising_constant; }
 uint64_t orc_drag_ambiguities(void *h) { return ((Decoder *)h)->t->drag_ambiguities; }
 uint64_t orc_radius_retries(void *h) { return ((Decoder *)h)->stat_radius_retries; }
+void orc_set_matcher_mode(void *h, int mode) { ((Decoder *)h)->matcher_mode = mode; }
 
 // Caller frees with orc_free_str.
 char *orc_describe(void *h) {
