@@ -32,50 +32,71 @@ struct CudaError : std::runtime_error {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
-// Device groups
+// Device groups: GROUP == 32 -> one warp per shot (4 shots per 128-thread block); otherwise one block of GROUP threads
+// per shot. Warp-level primitives serve the ball growth (one warp per ball).
 // ---------------------------------------------------------------------------------------------------------------
 template <int GROUP>
 struct DevGroup {
     int tid;
     int n;
+    int lane;
+    int lanes;
+    int warp;
+    int nwarps;
     __device__ __forceinline__ void sync() const {
-        if (GROUP == 1) {
-        } else if (GROUP == 32) {
-            __syncwarp();
-        } else {
-            __syncthreads();
+        if (GROUP == 32) __syncwarp();
+        else __syncthreads();
+    }
+    __device__ __forceinline__ void wsync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ uint32_t shfl32(uint32_t v, int src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
+    __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) const {
+        return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, src);
+    }
+    __device__ __forceinline__ uint64_t min64(uint64_t v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t w = (uint64_t)__shfl_xor_sync(0xFFFFFFFFu, (unsigned long long)v, o);
+            v = w < v ? w : v;
         }
+        return v;
     }
 };
 
-constexpr int BLOCK_THREADS = 128;
+constexpr int WARP_MODE_BLOCK = 128;  // threads per block when GROUP == 32
 
 template <int GROUP>
-__device__ __forceinline__ void group_ids(uint32_t &group, DevGroup<GROUP> &g) {
-    if (GROUP == 1) {
-        group = blockIdx.x * blockDim.x + threadIdx.x;
-        g.tid = 0;
-        g.n = 1;
-    } else if (GROUP == 32) {
-        group = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+__device__ __forceinline__ void group_ids(uint32_t &group, uint32_t &group_in_block, DevGroup<GROUP> &g) {
+    g.lane = threadIdx.x & 31;
+    g.lanes = 32;
+    if (GROUP == 32) {
+        group_in_block = threadIdx.x / 32;
+        group = blockIdx.x * (blockDim.x / 32) + group_in_block;
         g.tid = threadIdx.x & 31;
         g.n = 32;
+        g.warp = 0;
+        g.nwarps = 1;
     } else {
+        group_in_block = 0;
         group = blockIdx.x;
         g.tid = threadIdx.x;
-        g.n = blockDim.x;
+        g.n = GROUP;
+        g.warp = threadIdx.x >> 5;
+        g.nwarps = GROUP / 32;
     }
 }
 
+extern __shared__ __align__(16) uint8_t cb_smem[];
+
 // K0: establishes the persistent-clean invariants of every group's arena.
 template <int GROUP>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_init_arena(DecodeParams p, uint32_t num_groups) {
-    uint32_t group;
+__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP) k_init_arena(DecodeParams p, uint32_t num_groups) {
+    uint32_t group, gib;
     DevGroup<GROUP> g;
-    group_ids<GROUP>(group, g);
+    group_ids<GROUP>(group, gib, g);
     if (group >= num_groups) return;
     Shot s;
-    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, g);
+    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, cb_smem, g);
     init_group_arena(s, g);
 }
 
@@ -124,18 +145,20 @@ __global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict_
 
 // K2: the decode kernel. Persistent groups pull shots from a queue.
 template <int GROUP>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_decode(DecodeParams p, uint32_t num_groups) {
-    uint32_t group;
+__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP)
+    k_decode(DecodeParams p, uint32_t num_groups, uint32_t smem_per_group) {
+    uint32_t group, gib;
     DevGroup<GROUP> g;
-    group_ids<GROUP>(group, g);
+    group_ids<GROUP>(group, gib, g);
     if (group >= num_groups) return;
     Shot s;
-    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, g);
+    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, cb_smem + (size_t)gib * smem_per_group, g);
+    init_group_shared(s, g);
     const uint32_t total = p.shot_list ? p.list_len : p.num_shots;
     while (true) {
-        if (g.tid == 0) s.hdr->pad[0] = atomicAdd(p.work_counter, 1u);
+        if (g.tid == 0) s.hdr->bcast = atomicAdd(p.work_counter, 1u);
         g.sync();
-        uint32_t k = s.hdr->pad[0];
+        uint32_t k = s.hdr->bcast;
         g.sync();
         if (k >= total) break;
         uint32_t shot = p.shot_list ? p.shot_list[k] : k;
@@ -238,15 +261,35 @@ void upload_tables(cb200_decoder *d) {
 
 template <int GROUP>
 void launch_init(const DecodeParams &p, uint32_t groups, cudaStream_t st) {
-    uint32_t per_block = GROUP == 1 ? BLOCK_THREADS : (GROUP == 32 ? BLOCK_THREADS / 32 : 1);
+    uint32_t threads = GROUP == 32 ? WARP_MODE_BLOCK : GROUP;
+    uint32_t per_block = GROUP == 32 ? WARP_MODE_BLOCK / 32 : 1;
     uint32_t blocks = (groups + per_block - 1) / per_block;
-    k_init_arena<GROUP><<<blocks, BLOCK_THREADS, 0, st>>>(p, groups);
+    k_init_arena<GROUP><<<blocks, threads, 0, st>>>(p, groups);
 }
 template <int GROUP>
-void launch_decode(const DecodeParams &p, uint32_t groups, cudaStream_t st) {
-    uint32_t per_block = GROUP == 1 ? BLOCK_THREADS : (GROUP == 32 ? BLOCK_THREADS / 32 : 1);
+void launch_decode(const DecodeParams &p, uint32_t groups, uint32_t smem_per_group, cudaStream_t st) {
+    uint32_t threads = GROUP == 32 ? WARP_MODE_BLOCK : GROUP;
+    uint32_t per_block = GROUP == 32 ? WARP_MODE_BLOCK / 32 : 1;
     uint32_t blocks = (groups + per_block - 1) / per_block;
-    k_decode<GROUP><<<blocks, BLOCK_THREADS, 0, st>>>(p, groups);
+    size_t smem = (size_t)smem_per_group * per_block;
+    CUDA_CHECK(cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_decode<GROUP><<<blocks, threads, smem, st>>>(p, groups, smem_per_group);
+}
+template <int GROUP>
+int blocks_per_sm(size_t smem_per_group) {
+    uint32_t threads = GROUP == 32 ? WARP_MODE_BLOCK : GROUP;
+    uint32_t per_block = GROUP == 32 ? WARP_MODE_BLOCK / 32 : 1;
+    size_t smem = smem_per_group * per_block;
+    int n = 0;
+    if (cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_decode<GROUP>, (int)threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 const char *status_message(uint32_t st) {
@@ -268,6 +311,7 @@ const char *status_message(uint32_t st) {
 struct Plan {
     uint32_t group;
     uint32_t groups;
+    uint32_t smem_per_group;
     ScratchConfig cfg;
 };
 
@@ -275,27 +319,38 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     Plan pl{};
     uint32_t group = d->tune_group;
     if (group == 0) group = mean_det_events >= 24 ? 128 : 32;
-    if (group != 1 && group != 32 && group != 128) group = 32;
+    if (group != 32 && group != 128 && group != 256) group = 32;
     pl.group = group;
-    uint32_t ht = d->tune_ht_log2 ? d->tune_ht_log2 : 10;
-    ht += 3 * escalation;
-    uint32_t full = 1;
+    uint32_t full = 4;
     while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
-    if (ht > full) ht = full;
-    pl.cfg.ht_log2 = ht;
-    pl.cfg.heap_cap = 2u << ht;
-    pl.cfg.found_cap = 64u << (2 * escalation);
+    uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 9;
+    uint32_t gl = std::min<uint32_t>(full, 13 + 3 * escalation);
+    pl.cfg.sh_ht_log2 = std::min(sh, gl);
+    pl.cfg.sh_found = 24;
+    pl.cfg.ht_log2 = gl;
+    pl.cfg.found_cap = 256u << (2 * escalation);
     pl.cfg.max_events = std::max<uint32_t>(2 * max_det_events, 2);
     pl.cfg.dyn_bytes = ((uint64_t)(64 << 10) + (uint64_t)3072 * pl.cfg.max_events) << (3 * escalation);
-    uint32_t per_sm = group == 1 ? 256 : (group == 32 ? 16 : 4);
-    uint64_t want = (uint64_t)d->num_sms * per_sm;
-    if (escalation) want = std::min<uint64_t>(want, 64);
+    uint32_t nwarps = group == 32 ? 1 : group / 32;
+    pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
+    int per_sm = group == 32 ? blocks_per_sm<32>(pl.smem_per_group) * (WARP_MODE_BLOCK / 32)
+                             : (group == 128 ? blocks_per_sm<128>(pl.smem_per_group) : blocks_per_sm<256>(pl.smem_per_group));
+    if (per_sm <= 0) {
+        // the row does not fit beside the ball tables: drop the shared tables, keep the row
+        pl.cfg.sh_ht_log2 = 0;
+        pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
+        per_sm = group == 32 ? blocks_per_sm<32>(pl.smem_per_group) * (WARP_MODE_BLOCK / 32)
+                             : (group == 128 ? blocks_per_sm<128>(pl.smem_per_group) : blocks_per_sm<256>(pl.smem_per_group));
+        if (per_sm <= 0) throw std::invalid_argument("detector error model too large: one shot's row does not fit in shared memory");
+    }
+    uint64_t want = (uint64_t)d->num_sms * (uint32_t)per_sm;
     pl.groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, work_items));
     return pl;
 }
 
 void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &launches) {
-    uint64_t stride = arena_bytes_per_group(pl.cfg, d->dview.num_nodes, pl.group);
+    uint32_t nwarps = pl.group == 32 ? 1 : pl.group / 32;
+    uint64_t stride = arena_bytes_per_group(pl.cfg, d->dview.num_nodes, nwarps);
     bool same = d->arena_group == pl.group && d->arena_stride == stride && d->arena_groups >= pl.groups &&
                 memcmp(&d->arena_cfg, &pl.cfg, sizeof(ScratchConfig)) == 0;
     p.cfg = pl.cfg;
@@ -303,9 +358,9 @@ void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &l
     if (!same) {
         d->d_arena.ensure(stride * pl.groups);
         p.arena = d->d_arena.ptr;
-        if (pl.group == 1) launch_init<1>(p, pl.groups, d->stream);
-        else if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
-        else launch_init<128>(p, pl.groups, d->stream);
+        if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
+        else if (pl.group == 128) launch_init<128>(p, pl.groups, d->stream);
+        else launch_init<256>(p, pl.groups, d->stream);
         CUDA_CHECK(cudaGetLastError());
         launches++;
         d->arena_group = pl.group;
@@ -412,9 +467,9 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
             p.list_len = (uint32_t)retry.size();
             CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr + 4, 0, 4, s));
         }
-        if (pl.group == 1) launch_decode<1>(p, pl.groups, s);
-        else if (pl.group == 32) launch_decode<32>(p, pl.groups, s);
-        else launch_decode<128>(p, pl.groups, s);
+        if (pl.group == 32) launch_decode<32>(p, pl.groups, pl.smem_per_group, s);
+        else if (pl.group == 128) launch_decode<128>(p, pl.groups, pl.smem_per_group, s);
+        else launch_decode<256>(p, pl.groups, pl.smem_per_group, s);
         CUDA_CHECK(cudaGetLastError());
         launches++;
         if (esc == 0) CUDA_CHECK(cudaEventRecord(d->ev[3], s));
@@ -579,8 +634,8 @@ char *cb200_describe(const cb200_decoder *d) {
 void cb200_free_string(char *s) { free(s); }
 
 int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2) {
-    if (group_threads != 0 && group_threads != 1 && group_threads != 32 && group_threads != 128) {
-        g_error = "group_threads must be 0, 1, 32 or 128";
+    if (group_threads != 0 && group_threads != 32 && group_threads != 128 && group_threads != 256) {
+        g_error = "group_threads must be 0, 32, 128 or 256";
         return CB200_ERR_INVALID_ARGUMENT;
     }
     if (ht_log2 != 0 && (ht_log2 < 4 || ht_log2 > 24)) {

@@ -3,26 +3,28 @@
 //
 // Replaces, per shot (citations relative to /root/reference/src/chromobius):
 //   stage 1  lift-in            decode/decoder.cc:231-247   -> ingest_shot()
-//   stage 2  MWPM               decode/pymatcher.cc:27-42   -> match_shot()  (see "Matcher" below)
+//   stage 2  MWPM               decode/pymatcher.cc:27-42   -> match_shot() + paths_shot()  (see "Matcher" below)
 //   stage 3  Euler tours        graph/euler_tours.h:89-112, graph/euler_tours.cc:21-97 -> lift_shot()
 //   stage 4  discharge          decode/decoder.cc:80-203, 268-276                     -> lift_shot()
 //
 // Matcher. The reference delegates stage 2 to PyMatching's sparse blossom. A B200 wants independent work items, so
 // the matcher here is a *certified local* exact MWPM:
-//   1. every event grows a Dijkstra ball on the Moebius CSR until it has seen its nearest event(s)   [parallel/event]
-//   2. events that saw each other are merged into components (lock-free union-find)                  [parallel/event]
-//   3. each component is solved exactly by a dense primal-dual blossom on the seen pair distances    [parallel/component]
-//   4. the blossom duals certify the component against every UNSEEN pair: y_a <= R_a/2 for all a implies
+//   1. every event grows a Dijkstra ball on the Moebius CSR until it has seen its nearest event(s)   [one warp per ball]
+//   2. events that saw each other are merged into components (lock-free union-find)                  [thread per event]
+//   3. each component is solved exactly by a dense primal-dual blossom on the seen pair distances    [thread per component]
+//   4. the blossom duals certify the component against every UNSEEN pair: 2 y_a <= R_a for all a implies
 //      y_a + y_b <= max(R_a, R_b) < d(a, b) for unseen (a, b), i.e. the duals stay feasible on the complete event graph,
 //      so the union of the component matchings is a global minimum-weight perfect matching. Events whose dual is too
 //      large for their ball (or that sit in an odd / unmatched component) re-grow their ball and the affected
 //      components are re-solved. Typical shots need 2-5 rounds and components of 2-6 events.
-//   5. matched pairs are expanded into graph edges along a canonical shortest path.
+//   5. matched pairs are expanded into graph edges along a canonical shortest path                   [one warp per pair]
 // The total integer weight is exact (it is the optimum of the complete event graph); ties between equal-weight
 // matchings are broken by this file's own deterministic rules, not PyMatching's.
 //
-// Cooperative execution model: a *group* (1 thread, 1 warp or 1 block) decodes one shot. Loops over events /
-// components are strided by the group's thread id; `g.sync()` separates phases. The host build runs with a group of 1.
+// Cooperative execution model: a *group* (1 thread, 1 warp or 1 block) decodes one shot. Per-event / per-component
+// loops are strided by the group's thread id, ball growth is strided by warp with the 32 lanes relaxing one adjacency
+// row together; `g.sync()` separates phases. Ball tables (open-addressing hash + frontier) live in shared memory with
+// a per-warp global-memory fallback. The host build runs with a group of one thread and one lane.
 #ifndef CHROMOBIUS_B200_DECODE_CORE_H
 #define CHROMOBIUS_B200_DECODE_CORE_H
 
@@ -33,10 +35,8 @@
 
 #ifdef __CUDACC__
 #define CB_HD __host__ __device__ __forceinline__
-#define CB_D __device__
 #else
 #define CB_HD inline
-#define CB_D inline
 #endif
 
 namespace cb200 {
@@ -55,6 +55,8 @@ enum ShotStatus : uint32_t {
 constexpr uint32_t MAX_COMPONENT = 250;  // endpoints are stored as u8 in the blossom's edge matrix
 constexpr uint32_t MAX_ROUNDS = 64;
 constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t FRONT_CLOSED = 0xFFFFFFFFu;
+constexpr uint32_t SCAN_TMP = 1024;      // group sizes up to 1024 threads
 
 struct NbEntry {
     uint32_t ev;   // event index within the shot
@@ -62,12 +64,14 @@ struct NbEntry {
     int64_t d;     // exact shortest-path distance
 };
 
-// Sizes of the scratch carved out of one group's arena.
+// Sizes of the scratch of one group.
 struct ScratchConfig {
-    uint32_t ht_log2;     // Dijkstra hash table slots per thread = 1 << ht_log2
-    uint32_t heap_cap;    // Dijkstra heap entries per thread
-    uint32_t found_cap;   // events one ball may report
+    uint32_t sh_ht_log2;  // shared-memory ball table slots per warp = 1 << sh_ht_log2 (0: no shared tables)
+    uint32_t sh_found;    // events a ball may report from the shared-memory attempt
+    uint32_t ht_log2;     // global-memory fallback table slots per warp = 1 << ht_log2
+    uint32_t found_cap;   // events a ball may report from the fallback attempt
     uint32_t max_events;  // matcher events (2 x detection events) per shot the arena is sized for
+    uint32_t pad;
     uint64_t dyn_bytes;   // dynamic region (neighbour lists, blossom scratch, paths, Euler arrays)
 };
 
@@ -88,12 +92,12 @@ struct DecodeParams {
     uint64_t edge_dump_cap;
     uint64_t *edge_dump_len;
     // scratch
-    uint8_t *arena;              // num_groups * arena_stride bytes; persistent parts pre-initialised by init_arena
+    uint8_t *arena;              // num_groups * arena_stride bytes; persistent parts pre-initialised by init_group_arena
     uint64_t arena_stride;
     ScratchConfig cfg;
     uint32_t *work_counter;      // persistent-kernel shot queue
     // optional profiling: cycles spent by thread 0 of every group in
-    // [0] ingest [1] first exploration [2] component building [3] component solves [4] re-exploration
+    // [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
     // [5] path extraction [6] Euler tours + discharge [7] shots
     unsigned long long *phase_cycles;
 };
@@ -104,18 +108,18 @@ struct DecodeParams {
 #ifdef __CUDA_ARCH__
 CB_HD uint32_t cb_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { return atomicAdd((unsigned long long *)p, (unsigned long long)v); }
+CB_HD uint64_t cb_atomic_xor64(uint64_t *p, uint64_t v) { return atomicXor((unsigned long long *)p, (unsigned long long)v); }
 CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
 CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+CB_HD uint32_t cb_atomic_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
+CB_HD unsigned long long cb_clock() { return (unsigned long long)clock64(); }
 #else
 CB_HD uint32_t cb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { uint64_t o = *p; *p = o + v; return o; }
+CB_HD uint64_t cb_atomic_xor64(uint64_t *p, uint64_t v) { uint64_t o = *p; *p = o ^ v; return o; }
 CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { uint32_t o = *p; if (o == expect) *p = v; return o; }
 CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
-#endif
-
-#ifdef __CUDA_ARCH__
-CB_HD unsigned long long cb_clock() { return (unsigned long long)clock64(); }
-#else
+CB_HD uint32_t cb_atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 CB_HD unsigned long long cb_clock() { return 0; }
 #endif
 
@@ -133,19 +137,47 @@ struct PhaseTimer {
     }
 };
 
+// A group of one thread with one-lane "warps": the host simulation, and the device's thread-per-shot mode.
 struct HostGroup {
     int tid = 0;
     int n = 1;
+    int lane = 0;
+    int lanes = 1;
+    int warp = 0;
+    int nwarps = 1;
     CB_HD void sync() const {}
+    CB_HD void wsync() const {}
+    CB_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    CB_HD uint32_t shfl32(uint32_t v, int) const { return v; }
+    CB_HD uint64_t shfl64(uint64_t v, int) const { return v; }
+    CB_HD uint64_t min64(uint64_t v) const { return v; }
+    CB_HD uint64_t xor64(uint64_t v) const { return v; }
+    CB_HD uint64_t add64(uint64_t v) const { return v; }
 };
 
 CB_HD uint64_t align16(uint64_t x) { return (x + 15) & ~uint64_t{15}; }
+CB_HD uint32_t popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+CB_HD uint32_t ctz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// Arena layout of one group.
-//   [GroupHeader][per-thread Dijkstra scratch x n][node_slot: u32 x num_nodes][per-event arrays][dynamic region]
-// Persistent-clean invariants (established by init_group_arena, restored by every user):
-//   every Dijkstra hash key == HT_EMPTY, every node_slot == NO_INDEX.
+// Memory of one group.
+//   arena (global): [GroupHeader][scan_tmp][per-warp fallback ball tables][node_slot: u32 x num_nodes]
+//                   [per-event arrays][dynamic region]
+//   shared        : [masked row words][word ranks][per-warp ball tables]
+// Persistent-clean invariants (established by init_group_arena / init_group_shared, restored by every user):
+//   every ball-table key == HT_EMPTY, every node_slot == NO_INDEX.
 // ---------------------------------------------------------------------------------------------------------------
 struct GroupHeader {
     uint32_t status;
@@ -154,56 +186,75 @@ struct GroupHeader {
     uint32_t ngrow;
     uint64_t dyn_top;     // bump pointer (bytes from dyn base)
     uint64_t weight;      // total matched weight
-    uint32_t scan_tmp;
-    uint32_t pad[3];
+    uint64_t obs;         // XOR of the lifted cycles
+    uint32_t scan_total;
+    uint32_t bcast;
+    uint32_t lift_ncomp;
+    uint32_t lift_cyc_top;
+    uint32_t pad[2];
 };
 
-struct DijkScratch {
-    uint32_t *key;    // [H]
-    int64_t *dist;    // [H]
-    uint32_t *used;   // [H] slots inserted (for O(touched) clean-up)
-    int64_t *hd;      // heap distances
-    uint32_t *hn;     // heap nodes
-    NbEntry *found;   // [found_cap]
-    uint32_t H, hcap, fcap;
-    uint32_t nused, hsize;
+// Ball tables of one warp: open-addressing hash (node -> distance, frontier position) plus the frontier itself.
+struct BallTables {
+    uint32_t *key;     // [H]
+    int64_t *dist;     // [H]
+    uint32_t *fpos;    // [H] position in `front`, FRONT_CLOSED once settled
+    uint32_t *used;    // [cap] slots in insertion order (O(touched) clean-up)
+    uint32_t *front;   // [cap] slots of the open nodes
+    NbEntry *found;    // [fcap]
+    uint32_t H, cap, fcap;
+    uint32_t nused, nfront;
 };
 
-CB_HD uint64_t dijk_bytes(const ScratchConfig &c) {
-    uint64_t H = uint64_t{1} << c.ht_log2;
-    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(uint64_t{c.heap_cap} * 8) +
-           align16(uint64_t{c.heap_cap} * 4) + align16(uint64_t{c.found_cap} * sizeof(NbEntry));
+CB_HD uint64_t ball_table_bytes(uint32_t log2, uint32_t fcap) {
+    if (log2 == 0) return 0;
+    uint64_t H = uint64_t{1} << log2;
+    uint64_t cap = H * 3 / 4;
+    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(cap * 4) * 2 + align16(uint64_t{fcap} * sizeof(NbEntry));
+}
+CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t fcap) {
+    uint64_t H = uint64_t{1} << log2;
+    uint64_t cap = H * 3 / 4;
+    t.key = (uint32_t *)p; p += align16(H * 4);
+    t.dist = (int64_t *)p; p += align16(H * 8);
+    t.fpos = (uint32_t *)p; p += align16(H * 4);
+    t.used = (uint32_t *)p; p += align16(cap * 4);
+    t.front = (uint32_t *)p; p += align16(cap * 4);
+    t.found = (NbEntry *)p;
+    t.H = log2 ? (uint32_t)H : 0;
+    t.cap = (uint32_t)cap;
+    t.fcap = fcap;
+    t.nused = t.nfront = 0;
 }
 
 // Per-event arrays (all sized max_events), see struct Shot.
 CB_HD uint64_t event_bytes(const ScratchConfig &c) {
     uint64_t m = c.max_events;
-    // evdet(u32, m/2 -> m) R(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) uf root cnt start fillp members lidx
-    // comp_root path_off path_len (u32) dirty comp_dirty (u8) used_flag(u8)
+    // evdet(u32) R(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) + 9 x u32 + 3 x u8
     return align16(m * 4) + align16(m * 8) + align16(m * 4) * 2 + align16(m * 4) + align16(m * 8) + align16(m * 4) +
            align16(m * 4) * 9 + align16(m) * 3;
 }
-
-CB_HD uint64_t row_bytes(uint32_t num_dets) {
+CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets, uint32_t nwarps) {
     uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
-    return align16(nwords * 4) + align16((nwords + 1) * 4);
+    return align16(nwords * 4) + align16((nwords + 1) * 4) + nwarps * ball_table_bytes(c.sh_ht_log2, c.sh_found);
 }
-
-CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t group_threads) {
-    return align16(sizeof(GroupHeader)) + group_threads * dijk_bytes(c) + align16(uint64_t{num_nodes} * 4) +
-           row_bytes(num_nodes / 2) + event_bytes(c) + align16(c.dyn_bytes);
+CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t nwarps) {
+    return align16(sizeof(GroupHeader)) + align16(SCAN_TMP * 4) + nwarps * ball_table_bytes(c.ht_log2, c.found_cap) +
+           align16(uint64_t{num_nodes} * 4) + event_bytes(c) + align16(c.dyn_bytes);
 }
 
 // Everything one group needs to decode one shot. Every thread of the group holds an identical copy (pointers are
-// computed with the same arithmetic), except `dj`, which is the thread's own Dijkstra scratch.
+// computed with the same arithmetic), except the ball tables, which belong to the thread's warp.
 struct Shot {
     TablesView T;
     ScratchConfig cfg;
     GroupHeader *hdr;
-    DijkScratch dj;
+    uint32_t *scan_tmp;    // [SCAN_TMP]
+    BallTables sh_ball;    // this warp's shared-memory tables (H == 0: none)
+    BallTables gl_ball;    // this warp's global-memory fallback tables
     uint32_t *node_slot;   // [num_nodes] persistent-clean
-    uint32_t *words;       // masked detection-event bits as little-endian u32 words
-    uint32_t *word_rank;   // [nwords + 1] exclusive prefix popcount
+    uint32_t *words;       // masked detection-event bits as little-endian u32 words (shared memory)
+    uint32_t *word_rank;   // [nwords + 1] exclusive prefix popcount (shared memory)
     uint32_t nwords;
     uint32_t M;            // matcher events = 2 * detection events
     // per event
@@ -227,12 +278,7 @@ struct Shot {
     CB_HD uint32_t node_event_index(uint32_t node) const {
         uint32_t d = node >> 1;
         uint32_t w = words[d >> 5] & ((1u << (d & 31)) - 1);
-#ifdef __CUDA_ARCH__
-        uint32_t r = word_rank[d >> 5] + __popc(w);
-#else
-        uint32_t r = word_rank[d >> 5] + (uint32_t)__builtin_popcount(w);
-#endif
-        return 2 * r + (node & 1);
+        return 2 * (word_rank[d >> 5] + popc32(w)) + (node & 1);
     }
     CB_HD void fail(uint32_t code) const { cb_atomic_max(&hdr->status, code); }
     // Thread-safe bump allocation from the dynamic region; returns nullptr (and flags overflow) when exhausted.
@@ -248,30 +294,18 @@ struct Shot {
 };
 
 template <class G>
-CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, const G &g) {
+CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *shared, const G &g) {
     s.T = p.T;
     s.cfg = p.cfg;
     uint8_t *q = arena;
     s.hdr = (GroupHeader *)q;
     q += align16(sizeof(GroupHeader));
-    uint64_t H = uint64_t{1} << p.cfg.ht_log2;
-    uint8_t *mine = q + (uint64_t)g.tid * dijk_bytes(p.cfg);
-    s.dj.key = (uint32_t *)mine; mine += align16(H * 4);
-    s.dj.dist = (int64_t *)mine; mine += align16(H * 8);
-    s.dj.used = (uint32_t *)mine; mine += align16(H * 4);
-    s.dj.hd = (int64_t *)mine; mine += align16(uint64_t{p.cfg.heap_cap} * 8);
-    s.dj.hn = (uint32_t *)mine; mine += align16(uint64_t{p.cfg.heap_cap} * 4);
-    s.dj.found = (NbEntry *)mine;
-    s.dj.H = (uint32_t)H;
-    s.dj.hcap = p.cfg.heap_cap;
-    s.dj.fcap = p.cfg.found_cap;
-    s.dj.nused = 0;
-    s.dj.hsize = 0;
-    q += (uint64_t)g.n * dijk_bytes(p.cfg);
+    s.scan_tmp = (uint32_t *)q;
+    q += align16(SCAN_TMP * 4);
+    uint64_t gb = ball_table_bytes(p.cfg.ht_log2, p.cfg.found_cap);
+    bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp * gb, p.cfg.ht_log2, p.cfg.found_cap);
+    q += (uint64_t)g.nwarps * gb;
     s.node_slot = (uint32_t *)q; q += align16(uint64_t{p.T.num_nodes} * 4);
-    s.nwords = (p.T.num_dets + 31) / 32;
-    s.words = (uint32_t *)q; q += align16(uint64_t{s.nwords} * 4);
-    s.word_rank = (uint32_t *)q; q += align16((uint64_t{s.nwords} + 1) * 4);
     uint64_t m = p.cfg.max_events;
     s.evdet = (uint32_t *)q; q += align16(m * 4);
     s.R = (int64_t *)q; q += align16(m * 8);
@@ -289,35 +323,65 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, const G &g)
     s.dyn = q;
     s.dyn_cap = align16(p.cfg.dyn_bytes);
     s.M = 0;
+    // shared memory
+    s.nwords = (p.T.num_dets + 31) / 32;
+    uint8_t *sh = shared;
+    s.words = (uint32_t *)sh; sh += align16(uint64_t{s.nwords} * 4);
+    s.word_rank = (uint32_t *)sh; sh += align16((uint64_t{s.nwords} + 1) * 4);
+    uint64_t sb = ball_table_bytes(p.cfg.sh_ht_log2, p.cfg.sh_found);
+    bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, p.cfg.sh_ht_log2, p.cfg.sh_found);
 }
 
-// Called once per group before the first shot (and by the host after allocating a fresh arena).
+// Called once per group before the first shot of a launch (shared memory does not survive launches).
+template <class G>
+CB_HD void init_group_shared(Shot &s, const G &g) {
+    for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
+    g.sync();
+}
+// Called once per arena layout.
 template <class G>
 CB_HD void init_group_arena(Shot &s, const G &g) {
-    for (uint32_t k = 0; k < s.dj.H; k++) s.dj.key[k] = HT_EMPTY;
+    for (uint32_t k = g.lane; k < s.gl_ball.H; k += g.lanes) s.gl_ball.key[k] = HT_EMPTY;
     for (uint32_t k = g.tid; k < s.T.num_nodes; k += g.n) s.node_slot[k] = NO_INDEX;
     g.sync();
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Stage 1: lift-in (decode/decoder.cc:231-247). The masked row doubles as the node -> event index map.
-// Returns through s.M. Pad bits and ignored detectors are cleared by the ingest mask.
-// ---------------------------------------------------------------------------------------------------------------
-CB_HD uint32_t popc32(uint32_t v) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__popc(v);
-#else
-    return (uint32_t)__builtin_popcount(v);
-#endif
-}
-CB_HD uint32_t ctz32(uint32_t v) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)(__ffs((int)v) - 1);
-#else
-    return (uint32_t)__builtin_ctz(v);
-#endif
+// Exclusive prefix sum of arr[0..n) in place, cooperatively; returns the total. Needs g.n <= SCAN_TMP.
+template <class G>
+CB_HD uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t n) {
+    uint32_t chunk = (n + g.n - 1) / g.n;
+    uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; k++) sum += arr[k];
+    s.scan_tmp[g.tid] = sum;
+    g.sync();
+    if (g.tid == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < g.n; t++) {
+            uint32_t v = s.scan_tmp[t];
+            s.scan_tmp[t] = run;
+            run += v;
+        }
+        s.hdr->scan_total = run;
+    }
+    g.sync();
+    uint32_t run = s.scan_tmp[g.tid];
+    for (uint32_t k = lo; k < hi; k++) {
+        uint32_t v = arr[k];
+        arr[k] = run;
+        run += v;
+    }
+    uint32_t total = s.hdr->scan_total;
+    g.sync();
+    return total;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 1: lift-in (decode/decoder.cc:231-247). The masked row doubles as the node -> event index map.
+// Pad bits and ignored detectors are cleared by the ingest mask.
+// ---------------------------------------------------------------------------------------------------------------
 template <class G>
 CB_HD void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
     const uint32_t nb = s.T.num_det_bytes;
@@ -328,54 +392,30 @@ CB_HD void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
             if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
         }
         s.words[w] = v;
+        s.word_rank[w] = popc32(v);
     }
     if (g.tid == 0) {
         s.hdr->status = 0;
         s.hdr->dyn_top = 0;
         s.hdr->weight = 0;
+        s.hdr->obs = 0;
     }
     g.sync();
-    // exclusive prefix popcount: chunked, one serial pass over the per-thread sums
-    uint32_t chunk = (s.nwords + g.n - 1) / g.n;
-    uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
-    if (lo > s.nwords) lo = s.nwords;
-    if (hi > s.nwords) hi = s.nwords;
-    uint32_t sum = 0;
-    for (uint32_t w = lo; w < hi; w++) sum += popc32(s.words[w]);
-    // reuse `cnt` (per-event array, >= group size? not guaranteed) -> use uf scratch only if it fits; else serial
-    // Simple and robust: thread sums go to word_rank[lo] temporarily.
-    if (lo < hi) s.word_rank[lo] = sum;
-    g.sync();
-    if (g.tid == 0) {
-        uint32_t run = 0;
-        for (uint32_t t = 0; t < (uint32_t)g.n; t++) {
-            uint32_t tlo = t * chunk;
-            if (tlo >= s.nwords) break;
-            uint32_t v = s.word_rank[tlo];
-            s.word_rank[tlo] = run;
-            run += v;
-        }
-        s.word_rank[s.nwords] = run;
-        s.hdr->scan_tmp = run;
-    }
-    g.sync();
-    uint32_t total = s.hdr->scan_tmp;
+    uint32_t total = group_exclusive_scan(s, g, s.word_rank, s.nwords);
+    if (g.tid == 0) s.word_rank[s.nwords] = total;
     if (2 * total > s.cfg.max_events) {
         if (g.tid == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         s.M = 0;
         g.sync();
         return;
     }
-    if (lo < hi) {
-        uint32_t run = s.word_rank[lo];
-        for (uint32_t w = lo; w < hi; w++) {
-            s.word_rank[w] = run;
-            uint32_t v = s.words[w];
-            while (v) {
-                uint32_t b = ctz32(v);
-                v &= v - 1;
-                s.evdet[run++] = 32 * w + b;
-            }
+    for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
+        uint32_t run = s.word_rank[w];
+        uint32_t v = s.words[w];
+        while (v) {
+            uint32_t b = ctz32(v);
+            v &= v - 1;
+            s.evdet[run++] = 32 * w + b;
         }
     }
     s.M = 2 * total;
@@ -383,140 +423,182 @@ CB_HD void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Truncated Dijkstra on the Moebius CSR with a per-thread open-addressing table and a lazy binary heap.
+// Ball growth: truncated Dijkstra on the Moebius CSR, one warp per ball. The frontier is an unsorted list of hash
+// slots; the minimum is found by a warp reduction, the popped node's adjacency row is relaxed one lane per edge.
 // ---------------------------------------------------------------------------------------------------------------
-CB_HD uint32_t ht_hash(uint32_t node, uint32_t H) { return (node * 2654435761u) & (H - 1); }
+CB_HD uint32_t ht_hash(uint32_t node, uint32_t H) { return ((node ^ (node >> 7)) * 2654435761u) & (H - 1); }
 
-// Returns the slot of `node`, inserting it with dist = -1 when absent. Returns HT_EMPTY on table overflow.
-CB_HD uint32_t ht_slot(DijkScratch &dj, uint32_t node) {
-    uint32_t k = ht_hash(node ^ (node >> 7), dj.H);
+CB_HD int64_t ball_lookup(const BallTables &t, uint32_t node) {
+    uint32_t k = ht_hash(node, t.H);
     while (true) {
-        uint32_t cur = dj.key[k];
-        if (cur == node) return k;
-        if (cur == HT_EMPTY) {
-            if (dj.nused * 4 >= dj.H * 3) return HT_EMPTY;
-            dj.key[k] = node;
-            dj.dist[k] = -1;
-            dj.used[dj.nused++] = k;
-            return k;
-        }
-        k = (k + 1) & (dj.H - 1);
-    }
-}
-CB_HD int64_t ht_get(const DijkScratch &dj, uint32_t node) {
-    uint32_t k = ht_hash(node ^ (node >> 7), dj.H);
-    while (true) {
-        uint32_t cur = dj.key[k];
-        if (cur == node) return dj.dist[k];
+        uint32_t cur = t.key[k];
+        if (cur == node) return t.dist[k];
         if (cur == HT_EMPTY) return -1;
-        k = (k + 1) & (dj.H - 1);
+        k = (k + 1) & (t.H - 1);
     }
 }
-CB_HD void ht_clear(DijkScratch &dj) {
-    for (uint32_t k = 0; k < dj.nused; k++) dj.key[dj.used[k]] = HT_EMPTY;
-    dj.nused = 0;
-    dj.hsize = 0;
-}
-CB_HD bool heap_less(int64_t d1, uint32_t n1, int64_t d2, uint32_t n2) { return d1 < d2 || (d1 == d2 && n1 < n2); }
-CB_HD bool heap_push(DijkScratch &dj, int64_t d, uint32_t node) {
-    if (dj.hsize >= dj.hcap) return false;
-    uint32_t k = dj.hsize++;
-    while (k > 0) {
-        uint32_t p = (k - 1) >> 1;
-        if (!heap_less(d, node, dj.hd[p], dj.hn[p])) break;
-        dj.hd[k] = dj.hd[p];
-        dj.hn[k] = dj.hn[p];
-        k = p;
-    }
-    dj.hd[k] = d;
-    dj.hn[k] = node;
-    return true;
-}
-CB_HD void heap_pop(DijkScratch &dj, int64_t *d, uint32_t *node) {
-    *d = dj.hd[0];
-    *node = dj.hn[0];
-    uint32_t n = --dj.hsize;
-    if (n == 0) return;
-    int64_t ld = dj.hd[n];
-    uint32_t ln = dj.hn[n];
-    uint32_t k = 0;
-    while (true) {
-        uint32_t c = 2 * k + 1;
-        if (c >= n) break;
-        if (c + 1 < n && heap_less(dj.hd[c + 1], dj.hn[c + 1], dj.hd[c], dj.hn[c])) c++;
-        if (!heap_less(dj.hd[c], dj.hn[c], ld, ln)) break;
-        dj.hd[k] = dj.hd[c];
-        dj.hn[k] = dj.hn[c];
-        k = c;
-    }
-    dj.hd[k] = ld;
-    dj.hn[k] = ln;
+template <class G>
+CB_HD void ball_clear(BallTables &t, const G &g) {
+    g.wsync();
+    for (uint32_t k = g.lane; k < t.nused; k += g.lanes) t.key[t.used[k]] = HT_EMPTY;
+    t.nused = t.nfront = 0;
+    g.wsync();
 }
 
-// Grows the ball of event i.
-//   radius >= 0 : settle every node within `radius`, report every other event inside.
-//   radius <  0 : grow until more than `need_more_than` events have been seen, then finish that distance level.
-// Writes nb_off/nb_cnt/R of event i and marks i and every reported event dirty.
-CB_HD void explore_event(Shot &s, uint32_t i, int64_t radius, uint32_t need_more_than) {
-    DijkScratch &dj = s.dj;
-    const uint32_t src = s.event_node(i);
+enum BallResult : int { BALL_OK = 0, BALL_OVERFLOW = 1, BALL_EXHAUSTED = 2 };
+
+// Grows a ball around `src` (all lanes of the warp call this together; every lane returns the same values).
+//   radius >= 0 : settle every node within `radius`
+//   radius <  0 : grow until more than `need_more_than` events have been seen, then finish that distance level
+//   stop_node   : stop as soon as this node is settled (NO_INDEX: never)
+// Other events settled inside the ball are appended to t.found. The tables are left populated (caller clears).
+template <class G>
+CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int64_t radius, uint32_t need_more_than,
+                    uint32_t stop_node, bool collect_events, int64_t *limit_out, uint32_t *nfound_out) {
+    const uint32_t hmask = t.H - 1;
+    if (g.lane == 0) {
+        uint32_t k = ht_hash(src, t.H);
+        t.key[k] = src;
+        t.dist[k] = 0;
+        t.fpos[k] = 0;
+        t.used[0] = k;
+        t.front[0] = k;
+    }
+    t.nused = 1;
+    t.nfront = 1;
+    g.wsync();
     uint32_t nfound = 0;
     int64_t limit = radius;
-    bool ok = true;
-    uint32_t k0 = ht_slot(dj, src);
-    dj.dist[k0] = 0;
-    heap_push(dj, 0, src);
-    while (dj.hsize) {
-        int64_t d;
-        uint32_t u;
-        heap_pop(dj, &d, &u);
+    int result = BALL_OK;
+    while (t.nfront) {
+        // pop the closest open node
+        uint64_t best = ~uint64_t{0};
+        for (uint32_t q = g.lane; q < t.nfront; q += g.lanes) {
+            uint64_t cand = ((uint64_t)t.dist[t.front[q]] << 20) | q;
+            best = cand < best ? cand : best;
+        }
+        best = g.min64(best);
+        const int64_t d = (int64_t)(best >> 20);
+        const uint32_t q = (uint32_t)(best & 0xFFFFF);
         if (limit >= 0 && d > limit) break;
-        if (d != ht_get(dj, u)) continue;
-        if (u != src && s.node_is_event(u)) {
-            if (nfound >= dj.fcap) { ok = false; break; }
-            dj.found[nfound].ev = s.node_event_index(u);
-            dj.found[nfound].pad = 0;
-            dj.found[nfound].d = d;
+        const uint32_t slot = t.front[q];
+        const uint32_t u = t.key[slot];
+        g.wsync();
+        if (g.lane == 0) {
+            uint32_t last = t.front[t.nfront - 1];
+            t.front[q] = last;
+            t.fpos[last] = q;
+            t.fpos[slot] = FRONT_CLOSED;
+        }
+        t.nfront--;
+        g.wsync();
+        if (u == stop_node) break;
+        if (collect_events && u != src && s.node_is_event(u)) {
+            if (nfound >= t.fcap) {
+                result = BALL_OVERFLOW;
+                break;
+            }
+            if (g.lane == 0) {
+                t.found[nfound].ev = s.node_event_index(u);
+                t.found[nfound].pad = 0;
+                t.found[nfound].d = d;
+            }
             nfound++;
             if (limit < 0 && nfound > need_more_than) limit = d;
         }
-        const uint32_t e1 = s.T.row_ptr[u + 1];
-        for (uint32_t e = s.T.row_ptr[u]; e < e1; e++) {
-            AdjEntry a = s.T.adj[e];
-            int64_t nd = d + a.wt;
-            if (limit >= 0 && nd > limit) continue;
-            uint32_t k = ht_slot(dj, a.nbr);
-            if (k == HT_EMPTY) { ok = false; break; }
-            int64_t od = dj.dist[k];
-            if (od < 0 || nd < od) {
-                dj.dist[k] = nd;
-                if (!heap_push(dj, nd, a.nbr)) { ok = false; break; }
-            }
+        const uint32_t e0 = s.T.row_ptr[u], e1 = s.T.row_ptr[u + 1];
+        if (t.nused + (e1 - e0) > t.cap || t.nused + (e1 - e0) >= (1u << 20)) {
+            result = BALL_OVERFLOW;
+            break;
         }
-        if (!ok) break;
+        for (uint32_t base = e0; base < e1; base += g.lanes) {
+            const uint32_t e = base + g.lane;
+            bool is_new = false;
+            uint32_t my_slot = 0;
+            if (e < e1) {
+                AdjEntry a = s.T.adj[e];
+                int64_t nd = d + a.wt;
+                if (!(limit >= 0 && nd > limit)) {
+                    uint32_t k = ht_hash(a.nbr, t.H);
+                    while (true) {
+                        uint32_t old = cb_atomic_cas(&t.key[k], HT_EMPTY, a.nbr);
+                        if (old == HT_EMPTY) {
+                            is_new = true;
+                            break;
+                        }
+                        if (old == a.nbr) break;
+                        k = (k + 1) & hmask;
+                    }
+                    my_slot = k;
+                    if (is_new) t.dist[k] = nd;
+                    else if (t.fpos[k] != FRONT_CLOSED && nd < t.dist[k]) t.dist[k] = nd;
+                }
+            }
+            const uint32_t fresh = g.ballot(is_new);
+            if (is_new) {
+                uint32_t idx = popc32(fresh & ((1u << g.lane) - 1));
+                t.used[t.nused + idx] = my_slot;
+                t.front[t.nfront + idx] = my_slot;
+                t.fpos[my_slot] = t.nfront + idx;
+            }
+            const uint32_t c = popc32(fresh);
+            t.nused += c;
+            t.nfront += c;
+            g.wsync();
+        }
     }
-    ht_clear(dj);
-    if (!ok) {
-        s.fail(SHOT_SCRATCH_OVERFLOW);
-        return;
-    }
-    if (limit < 0) {
-        // Nothing more is reachable: this event cannot be paired (odd component of the Moebius graph).
-        s.fail(SHOT_NO_PERFECT_MATCHING);
-        return;
-    }
-    NbEntry *dst = (NbEntry *)s.alloc(uint64_t{nfound} * sizeof(NbEntry) + 16);
-    if (!dst) return;
-    for (uint32_t k = 0; k < nfound; k++) {
-        dst[k] = dj.found[k];
-        s.dirty[dj.found[k].ev] = 1;
-    }
-    s.dirty[i] = 1;
-    s.nb_off[i] = (uint32_t)(((uint8_t *)dst - s.dyn) >> 4);
-    s.nb_cnt[i] = nfound;
-    s.R[i] = limit;
+    if (result == BALL_OK && limit < 0) result = BALL_EXHAUSTED;
+    *limit_out = limit;
+    *nfound_out = nfound;
+    return result;
 }
+
 CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry *)(s.dyn + ((uint64_t)s.nb_off[i] << 4)); }
+
+// Grows the ball of event i (one warp). Writes nb_off/nb_cnt/R of event i and marks i and every reported event dirty.
+template <class G>
+CB_HD void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
+    const uint32_t src = s.event_node(i);
+    int64_t limit = 0;
+    uint32_t nfound = 0;
+    BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
+    int r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, &limit, &nfound);
+    if (r == BALL_OVERFLOW && t == &s.sh_ball) {
+        ball_clear(*t, g);
+        t = &s.gl_ball;
+        r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, &limit, &nfound);
+    }
+    ball_clear(*t, g);
+    if (r == BALL_OVERFLOW) {
+        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        return;
+    }
+    if (r == BALL_EXHAUSTED) {
+        // Nothing more is reachable: this event cannot be paired (odd component of the Moebius graph).
+        if (g.lane == 0) s.fail(SHOT_NO_PERFECT_MATCHING);
+        return;
+    }
+    uint64_t off = 0;
+    if (g.lane == 0) {
+        uint8_t *dst = s.alloc(uint64_t{nfound} * sizeof(NbEntry) + 16);
+        off = dst ? (uint64_t)(dst - s.dyn) + 1 : 0;
+    }
+    off = g.shfl64(off, 0);
+    if (!off) return;
+    NbEntry *dst = (NbEntry *)(s.dyn + (off - 1));
+    for (uint32_t k = g.lane; k < nfound; k += g.lanes) {
+        NbEntry e = t->found[k];
+        dst[k] = e;
+        s.dirty[e.ev] = 1;
+    }
+    if (g.lane == 0) {
+        s.dirty[i] = 1;
+        s.nb_off[i] = (uint32_t)((off - 1) >> 4);
+        s.nb_cnt[i] = nfound;
+        s.R[i] = limit;
+    }
+    g.wsync();
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Dense primal-dual blossom (maximum weight among maximum-cardinality matchings) over one component.
@@ -1003,7 +1085,7 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         s.used_flag[i] = 0;
     }
     g.sync();
-    for (uint32_t i = g.tid; i < M; i += g.n) explore_event(s, i, -1, 0);
+    for (uint32_t i = g.warp; i < M; i += g.nwarps) explore_event(s, g, i, -1, 0);
     uint32_t round = 0;
     while (true) {
         g.sync();
@@ -1066,9 +1148,9 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         g.sync();  // everyone has read the verdict before the next phase may change it
         if (st) return round;
         if (ngrow == 0) return round;
-        for (uint32_t k = g.tid; k < ngrow; k += g.n) {
+        for (uint32_t k = g.warp; k < ngrow; k += g.nwarps) {
             uint32_t ev = s.grow_ev[k];
-            explore_event(s, ev, s.grow_to[k], s.nb_cnt[ev]);
+            explore_event(s, g, ev, s.grow_to[k], s.nb_cnt[ev]);
         }
     }
 }
@@ -1076,100 +1158,116 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 // ---------------------------------------------------------------------------------------------------------------
 // Matched pair -> graph edges along the canonical shortest path: among equal-length paths, walking back from the
 // larger event index towards the smaller one always steps to the smallest-id tight predecessor. Stored as the node
-// sequence src .. dst in the dynamic region.
+// sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
-CB_HD void extract_path(Shot &s, uint32_t i, uint32_t j, int64_t d_total) {
-    DijkScratch &dj = s.dj;
+template <class G>
+CB_HD void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_total) {
     const uint32_t src = s.event_node(i), dst = s.event_node(j);
-    bool ok = true;
-    uint32_t k0 = ht_slot(dj, src);
-    dj.dist[k0] = 0;
-    heap_push(dj, 0, src);
-    while (dj.hsize) {
-        int64_t d;
-        uint32_t u;
-        heap_pop(dj, &d, &u);
-        if (d != ht_get(dj, u)) continue;
-        if (u == dst) break;  // every node closer than d_total is settled; weights are positive
-        const uint32_t e1 = s.T.row_ptr[u + 1];
-        for (uint32_t e = s.T.row_ptr[u]; e < e1; e++) {
-            AdjEntry a = s.T.adj[e];
-            int64_t nd = d + a.wt;
-            if (nd > d_total) continue;
-            uint32_t k = ht_slot(dj, a.nbr);
-            if (k == HT_EMPTY) { ok = false; break; }
-            int64_t od = dj.dist[k];
-            if (od < 0 || nd < od) {
-                dj.dist[k] = nd;
-                if (!heap_push(dj, nd, a.nbr)) { ok = false; break; }
-            }
-        }
-        if (!ok) break;
+    int64_t limit = 0;
+    uint32_t nfound = 0;
+    BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
+    int r = ball_grow(s, g, *t, src, d_total, 0, dst, false, &limit, &nfound);
+    if (r == BALL_OVERFLOW && t == &s.sh_ball) {
+        ball_clear(*t, g);
+        t = &s.gl_ball;
+        r = ball_grow(s, g, *t, src, d_total, 0, dst, false, &limit, &nfound);
     }
-    uint32_t len = 0;
+    bool ok = r == BALL_OK;
+    uint32_t len = 1;
     uint32_t *out = nullptr;
-    if (ok) {
-        // two walks: count, then fill back to front
-        for (int pass = 0; pass < 2 && ok; pass++) {
-            uint32_t cur = dst;
-            int64_t dc = d_total;
-            uint32_t pos = len;
-            if (pass == 1) out[--pos] = cur;
-            else len = 1;
-            while (cur != src) {
-                uint32_t best = NO_INDEX;
-                int64_t bd = 0;
-                const uint32_t e1 = s.T.row_ptr[cur + 1];
-                for (uint32_t e = s.T.row_ptr[cur]; e < e1; e++) {
+    // two walks: count, then fill back to front
+    for (int pass = 0; pass < 2 && ok; pass++) {
+        uint32_t cur = dst;
+        int64_t dc = d_total;
+        uint32_t pos = len;
+        if (pass == 1 && g.lane == 0) out[pos - 1] = cur;
+        pos--;
+        uint32_t steps = 0;
+        while (cur != src) {
+            const uint32_t e0 = s.T.row_ptr[cur], e1 = s.T.row_ptr[cur + 1];
+            uint32_t best = NO_INDEX;
+            int64_t bd = 0;
+            for (uint32_t base = e0; base < e1 && best == NO_INDEX; base += g.lanes) {
+                uint32_t e = base + g.lane;
+                bool hit = false;
+                int64_t dv = -1;
+                uint32_t nbr = 0;
+                if (e < e1) {
                     AdjEntry a = s.T.adj[e];
-                    int64_t dv = ht_get(dj, a.nbr);
-                    if (dv >= 0 && dv + a.wt == dc) {
-                        best = a.nbr;
-                        bd = dv;
-                        break;
-                    }
+                    nbr = a.nbr;
+                    dv = ball_lookup(*t, nbr);
+                    hit = dv >= 0 && dv + a.wt == dc;
                 }
-                if (best == NO_INDEX) { ok = false; break; }
-                cur = best;
-                dc = bd;
-                if (pass == 1) out[--pos] = cur;
-                else len++;
+                uint32_t hits = g.ballot(hit);
+                if (hits) {
+                    int first = (int)ctz32(hits);  // rows are sorted by neighbour id: the first hit is the smallest id
+                    best = g.shfl32(nbr, first);
+                    bd = (int64_t)g.shfl64((uint64_t)dv, first);
+                }
             }
-            if (pass == 0 && ok) {
-                out = (uint32_t *)s.alloc(uint64_t{len} * 4);
-                if (!out) { ok = false; ht_clear(dj); return; }
+            if (best == NO_INDEX || ++steps > s.T.num_nodes) {
+                ok = false;
+                break;
             }
+            cur = best;
+            dc = bd;
+            if (pass == 1 && g.lane == 0) out[pos - 1] = cur;
+            pos--;
+            if (pass == 0) len++;
+        }
+        if (pass == 0 && ok) {
+            uint64_t off = 0;
+            if (g.lane == 0) {
+                uint8_t *mem = s.alloc(uint64_t{len} * 4);
+                off = mem ? (uint64_t)(mem - s.dyn) + 1 : 0;
+            }
+            off = g.shfl64(off, 0);
+            if (!off) {
+                ball_clear(*t, g);
+                return;  // alloc already flagged the overflow
+            }
+            out = (uint32_t *)(s.dyn + (off - 1));
         }
     }
-    ht_clear(dj);
+    ball_clear(*t, g);
     if (!ok) {
-        s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
-    s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
-    s.path_len[i] = len;
+    if (g.lane == 0) {
+        s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
+        s.path_len[i] = len;
+    }
+    g.wsync();
 }
 
 template <class G>
 CB_HD void paths_shot(Shot &s, const G &g) {
+    for (uint32_t i = g.tid; i < s.M; i += g.n) s.path_len[i] = 0;
+    g.sync();
     uint64_t wsum = 0;
-    for (uint32_t i = g.tid; i < s.M; i += g.n) {
+    for (uint32_t i = g.warp; i < s.M; i += g.nwarps) {
         int32_t j = s.partner[i];
-        s.path_len[i] = 0;
         if (j > (int32_t)i) {
             int64_t d = seen_distance(s, i, (uint32_t)j);
             wsum += (uint64_t)d;
-            extract_path(s, i, (uint32_t)j, d);
+            extract_path(s, g, i, (uint32_t)j, d);
         }
     }
-    if (wsum) cb_atomic_add64(&s.hdr->weight, wsum);
+    if (wsum && g.lane == 0) cb_atomic_add64(&s.hdr->weight, wsum);
     g.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stages 3 + 4, one thread per shot: Euler tours (graph/euler_tours.h:89-112, euler_tours.cc:21-97) over
-// matched edges + one doubling edge per detection event, each closed tour discharged through the drag table
-// (decode/decoder.cc:80-203) and XOR-ed into the prediction (decoder.cc:268-276).
+// Stages 3 + 4: Euler tours (graph/euler_tours.h:89-112, euler_tours.cc:21-97) over matched edges + one doubling
+// edge per detection event, each closed tour discharged through the drag table (decode/decoder.cc:80-203) and
+// XOR-ed into the prediction (decoder.cc:268-276).
+//
+// The reference builds per-node neighbour lists in edge-list order and burns components in the order their first node
+// appears in the matcher's edge list. Components are independent, so here every connected component is toured by its
+// own thread; its neighbour lists hold the half-edges in the same (edge-list) order and its tour starts at the same
+// node, which makes each cycle identical to the reference's and the XOR of the cycle results order independent.
+// Half-edge q = 2 * edge + side; edges are numbered in emission order, matched edges first, then doubling edges.
 // ---------------------------------------------------------------------------------------------------------------
 struct OptMask {
     uint64_t v[4];
@@ -1253,162 +1351,202 @@ CB_HD bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len, 
     return false;
 }
 
-struct HalfEdge {
-    uint32_t node;   // NO_INDEX = voided
-    uint32_t back;   // position of the reverse half-edge in the other node's list
+struct LiftArrays {
+    uint32_t *own;      // [HE] node at this end of half-edge q
+    uint32_t *slot;     // [HE] id of own[q]'s adjacency list (= smallest half-edge at that node)
+    uint32_t *lstart;   // [HE + 1] list start per slot id (exclusive scan of degrees)
+    uint32_t *fillc;    // [HE] insertion counters, later the tour cursor (look_next_neighbor state)
+    uint32_t *lst;      // [HE] half-edges grouped by list, ascending q inside a list
+    uint32_t *pos_of;   // [HE] position of half-edge q in lst
+    uint32_t *uf;       // [HE] union-find over slot ids
+    uint32_t *cmin;     // [HE] per component root: smallest matched half-edge (tour start)
+    uint32_t *cedges;   // [HE] per component root: number of edges
+    uint32_t *comps;    // [HE] list of component roots
+    uint32_t *cyc;      // cycle buffers
+    uint8_t *dead;      // [HE] voided list positions
+    uint32_t HE, EM;    // half-edges, matched edges
 };
 
-// Runs on one thread. Returns false after setting the status on failure.
-CB_HD bool lift_shot(Shot &s, uint64_t *obs_out, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
-    const uint32_t M = s.M;
-    // count edges
-    uint32_t nedges = M / 2;
-    for (uint32_t i = 0; i < M; i++)
-        if (s.path_len[i]) nedges += s.path_len[i] - 1;
-    uint32_t *slot_node = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);   // local id -> node
-    uint32_t *deg = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);         // then: list start
-    uint32_t *fill = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);        // then: next_neighbor cursor
-    uint32_t *lend = (uint32_t *)s.alloc(uint64_t{nedges} * 2 * 4 + 16);
-    HalfEdge *he = (HalfEdge *)s.alloc(uint64_t{nedges} * 2 * sizeof(HalfEdge) + 16);
-    uint32_t *cyc = (uint32_t *)s.alloc((uint64_t{nedges} + 4) * 4);
-    if (!slot_node || !deg || !fill || !lend || !he || !cyc) return false;
-    uint32_t nslots = 0;
-    auto slot_of = [&](uint32_t node) -> uint32_t {
-        uint32_t k = s.node_slot[node];
-        if (k == NO_INDEX) {
-            k = nslots++;
-            s.node_slot[node] = k;
-            slot_node[k] = node;
-            deg[k] = 0;
-        }
-        return k;
-    };
-    // pass 1: degrees (matched edges in emission order, then doubling edges)
-    for (uint32_t i = 0; i < M; i++) {
-        uint32_t len = s.path_len[i];
-        if (!len) continue;
-        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
-        for (uint32_t k = 0; k + 1 < len; k++) {
-            deg[slot_of(p[k])]++;
-            deg[slot_of(p[k + 1])]++;
-        }
-    }
-    for (uint32_t i = 0; i < M; i += 2) {
-        deg[slot_of(s.event_node(i))]++;
-        deg[slot_of(s.event_node(i + 1))]++;
-    }
-    uint32_t run = 0;
-    for (uint32_t k = 0; k < nslots; k++) {
-        uint32_t dg = deg[k];
-        deg[k] = run;       // list start
-        fill[k] = run;      // insertion cursor
-        run += dg;
-        lend[k] = run;
-    }
-    uint64_t dumped = 0;
-    auto add_edge = [&](uint32_t a, uint32_t b) {
-        uint32_t sa = s.node_slot[a], sb = s.node_slot[b];
-        uint32_t pa_ = fill[sa]++, pb_ = fill[sb]++;
-        he[pa_].node = b;
-        he[pa_].back = pb_;
-        he[pb_].node = a;
-        he[pb_].back = pa_;
-    };
-    for (uint32_t i = 0; i < M; i++) {
-        uint32_t len = s.path_len[i];
-        if (!len) continue;
-        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
-        for (uint32_t k = 0; k + 1 < len; k++) {
-            add_edge(p[k], p[k + 1]);
-            if (edge_dump) {
-                if (dumped + 2 <= edge_dump_cap) {
-                    edge_dump[dumped] = p[k];
-                    edge_dump[dumped + 1] = p[k + 1];
-                }
-                dumped += 2;
-            }
-        }
-    }
-    if (edge_dump_len) *edge_dump_len = dumped;
-    for (uint32_t i = 0; i < M; i += 2) add_edge(s.event_node(i), s.event_node(i + 1));
-    // cursors restart at the list heads (next_neighbor = 0)
-    for (uint32_t k = 0; k < nslots; k++) fill[k] = deg[k];
+// Tours and discharges one component. Runs on one thread.
+CB_HD void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc) {
     auto look_next = [&](uint32_t sl) -> uint32_t {  // euler_tours.cc:34-45
         while (true) {
-            if (fill[sl] >= lend[sl]) return NO_INDEX;
-            if (he[fill[sl]].node == NO_INDEX) {
-                fill[sl]++;
+            uint32_t p = L.lstart[sl] + L.fillc[sl];
+            if (p >= L.lstart[sl + 1]) return NO_INDEX;
+            if (L.dead[p]) {
+                L.fillc[sl]++;
                 continue;
             }
-            return fill[sl];
+            return p;
         }
     };
-    uint64_t solution = 0;
-    bool ok = true;
-    uint32_t code = 0;
-    // burn components in matched-edge-list order (euler_tours.h:104-106)
-    for (uint32_t i = 0; i < M && ok; i++) {
+    uint32_t n0 = L.own[L.cmin[root]];
+    uint32_t clen = 0;
+    cyc[clen++] = n0;
+    while (true) {
+        // extend_cycle_depth_first (euler_tours.cc:64-76)
+        while (true) {
+            uint32_t sl = s.node_slot[cyc[clen - 1]];
+            uint32_t p = look_next(sl);
+            if (p == NO_INDEX) break;
+            L.fillc[sl]++;
+            uint32_t q = L.lst[p];
+            cyc[clen++] = L.own[q ^ 1];
+            L.dead[L.pos_of[q ^ 1]] = 1;
+        }
+        // rotate_cycle_to_end_with_unfinished_node (euler_tours.cc:78-97)
+        if (cyc[clen - 1] != cyc[0]) {
+            s.fail(SHOT_EULER_FAILED);
+            return;
+        }
+        clen--;
+        uint32_t ck = 1;
+        while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
+        if (ck >= clen) break;
+        // cyc = cyc[ck:] + cyc[:ck+1]
+        for (uint32_t a = 0, b = ck - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+        for (uint32_t a = ck, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+        for (uint32_t a = 0, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
+        cyc[clen] = cyc[0];
+        clen++;
+    }
+    // discharge_cycle (decoder.cc:140-203): start charges N, R, G, B; the first that closes wins
+    for (uint32_t c = 0; c < 4; c++) {
+        uint64_t v;
+        if (discharge_single_start(s, cyc, clen, c, &v)) {
+            if (v) cb_atomic_xor64(&s.hdr->obs, v);
+            return;
+        }
+    }
+    s.fail(SHOT_DISCHARGE_FAILED);
+}
+
+template <class G>
+CB_HD void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
+    const uint32_t M = s.M;
+    // edge numbering: exclusive scan of (path_len - 1) over events -> s.start
+    for (uint32_t i = g.tid; i < M; i += g.n) s.start[i] = s.path_len[i] ? s.path_len[i] - 1 : 0;
+    g.sync();
+    LiftArrays L;
+    L.EM = group_exclusive_scan(s, g, s.start, M);
+    const uint32_t E = L.EM + M / 2;
+    L.HE = 2 * E;
+    const uint32_t HE = L.HE;
+    if (g.tid == 0) {
+        uint8_t *mem = s.alloc((uint64_t{HE} * 10 + 1) * 4 + 16 * 12 + (uint64_t{3} * E + 8) * 4 + HE);
+        s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
+        s.hdr->lift_ncomp = 0;
+        s.hdr->lift_cyc_top = 0;
+        if (edge_dump_len) *edge_dump_len = 2 * (uint64_t)L.EM;
+    }
+    g.sync();
+    const uint32_t moff = s.hdr->scan_total;
+    g.sync();
+    if (!moff) return;
+    {
+        uint8_t *p = s.dyn + ((uint64_t)(moff - 1) << 4);
+        uint32_t **arrs[] = {&L.own, &L.slot, &L.fillc, &L.lst, &L.pos_of, &L.uf, &L.cmin, &L.cedges, &L.comps};
+        for (auto a : arrs) { *a = (uint32_t *)p; p += align16(uint64_t{HE} * 4); }
+        L.lstart = (uint32_t *)p; p += align16((uint64_t{HE} + 1) * 4);
+        L.cyc = (uint32_t *)p; p += align16((uint64_t{3} * E + 8) * 4);
+        L.dead = p;
+    }
+    // a. endpoints of every half-edge
+    for (uint32_t i = g.tid; i < M; i += g.n) {
         uint32_t len = s.path_len[i];
-        if (!len) continue;
-        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
-        for (uint32_t k = 0; k + 1 < len && ok; k++) {
-            for (uint32_t side = 0; side < 2 && ok; side++) {
-                uint32_t n0 = p[k + side];
-                if (look_next(s.node_slot[n0]) == NO_INDEX) continue;
-                uint32_t clen = 0;
-                cyc[clen++] = n0;
-                while (true) {
-                    // extend_cycle_depth_first (euler_tours.cc:64-76)
-                    while (true) {
-                        uint32_t sl = s.node_slot[cyc[clen - 1]];
-                        uint32_t h = look_next(sl);
-                        if (h == NO_INDEX) break;
-                        fill[sl]++;
-                        HalfEdge e = he[h];
-                        cyc[clen++] = e.node;
-                        he[e.back].node = NO_INDEX;
-                    }
-                    // rotate_cycle_to_end_with_unfinished_node (euler_tours.cc:78-97)
-                    if (cyc[clen - 1] != cyc[0]) {
-                        ok = false;
-                        code = SHOT_EULER_FAILED;
-                        break;
-                    }
-                    clen--;
-                    uint32_t ck = 1;
-                    while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
-                    if (ck >= clen) break;
-                    // cyc = cyc[ck:] + cyc[:ck+1]
-                    for (uint32_t a = 0, b = ck - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-                    for (uint32_t a = ck, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-                    for (uint32_t a = 0, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-                    cyc[clen] = cyc[0];
-                    clen++;
-                }
-                if (!ok) break;
-                // discharge_cycle (decoder.cc:140-203): start charges N, R, G, B; first that closes wins
-                bool lifted = false;
-                for (uint32_t c = 0; c < 4 && !lifted; c++) {
-                    uint64_t v;
-                    if (discharge_single_start(s, cyc, clen, c, &v)) {
-                        solution ^= v;
-                        lifted = true;
-                    }
-                }
-                if (!lifted) {
-                    ok = false;
-                    code = SHOT_DISCHARGE_FAILED;
+        if (len) {
+            const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+            uint32_t e = s.start[i];
+            for (uint32_t k = 0; k + 1 < len; k++, e++) {
+                L.own[2 * e] = p[k];
+                L.own[2 * e + 1] = p[k + 1];
+                if (edge_dump && 2 * (uint64_t)e + 2 <= edge_dump_cap) {
+                    edge_dump[2 * e] = p[k];
+                    edge_dump[2 * e + 1] = p[k + 1];
                 }
             }
         }
+        if ((i & 1) == 0) {
+            uint32_t e = L.EM + i / 2;
+            L.own[2 * e] = s.event_node(i);
+            L.own[2 * e + 1] = s.event_node(i + 1);
+        }
     }
-    for (uint32_t k = 0; k < nslots; k++) s.node_slot[slot_node[k]] = NO_INDEX;
-    if (!ok) {
-        s.fail(code);
-        return false;
+    g.sync();
+    // b. list id of a node = its smallest half-edge
+    for (uint32_t q = g.tid; q < HE; q += g.n) {
+        cb_atomic_min(&s.node_slot[L.own[q]], q);
+        L.lstart[q] = 0;
+        L.fillc[q] = 0;
+        L.uf[q] = q;
+        L.cmin[q] = NO_INDEX;
+        L.cedges[q] = 0;
+        L.dead[q] = 0;
     }
-    *obs_out = solution;
-    return true;
+    g.sync();
+    // c. degrees and connectivity
+    for (uint32_t q = g.tid; q < HE; q += g.n) {
+        uint32_t sl = s.node_slot[L.own[q]];
+        L.slot[q] = sl;
+        cb_atomic_add(&L.lstart[sl], 1);
+    }
+    g.sync();
+    for (uint32_t e = g.tid; e < E; e += g.n) uf_union(L.uf, L.slot[2 * e], L.slot[2 * e + 1]);
+    g.sync();
+    // d. list offsets
+    uint32_t total = group_exclusive_scan(s, g, L.lstart, HE);
+    if (g.tid == 0) L.lstart[HE] = total;
+    g.sync();
+    // e. fill
+    for (uint32_t q = g.tid; q < HE; q += g.n) {
+        uint32_t sl = L.slot[q];
+        uint32_t p = L.lstart[sl] + cb_atomic_add(&L.fillc[sl], 1);
+        L.lst[p] = q;
+    }
+    g.sync();
+    // f. restore edge-list order inside every list; component bookkeeping
+    for (uint32_t q = g.tid; q < HE; q += g.n) {
+        if (L.slot[q] == q) {
+            uint32_t a0 = L.lstart[q], a1 = L.lstart[q + 1];
+            for (uint32_t a = a0 + 1; a < a1; a++) {
+                uint32_t v = L.lst[a];
+                uint32_t b = a;
+                while (b > a0 && L.lst[b - 1] > v) {
+                    L.lst[b] = L.lst[b - 1];
+                    b--;
+                }
+                L.lst[b] = v;
+            }
+            for (uint32_t a = a0; a < a1; a++) L.pos_of[L.lst[a]] = a;
+            L.fillc[q] = 0;  // becomes next_neighbor
+        }
+        uint32_t r = uf_find(L.uf, L.slot[q]);
+        if (q < 2 * L.EM) cb_atomic_min(&L.cmin[r], q);
+        if ((q & 1) == 0) cb_atomic_add(&L.cedges[r], 1);
+    }
+    g.sync();
+    // g. component list and cycle buffers
+    for (uint32_t q = g.tid; q < HE; q += g.n)
+        if (L.slot[q] == q && uf_find(L.uf, q) == q) {
+            uint32_t k = cb_atomic_add(&s.hdr->lift_ncomp, 1);
+            L.comps[k] = q;
+        }
+    g.sync();
+    const uint32_t ncomp = s.hdr->lift_ncomp;
+    // h. one thread per component
+    for (uint32_t c = g.tid; c < ncomp; c += g.n) {
+        uint32_t root = L.comps[c];
+        uint32_t off = cb_atomic_add(&s.hdr->lift_cyc_top, L.cedges[root] + 2);
+        if (L.cmin[root] == NO_INDEX) {
+            s.fail(SHOT_EULER_FAILED);
+            continue;
+        }
+        lift_component(s, L, root, L.cyc + off);
+    }
+    g.sync();
+    // i. restore the persistent-clean node_slot array
+    for (uint32_t q = g.tid; q < HE; q += g.n) s.node_slot[L.own[q]] = NO_INDEX;
+    g.sync();
 }
 
 // One shot, start to finish. `shot` indexes the caller's arrays.
@@ -1425,10 +1563,12 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
     }
     g.sync();
     pt.lap(5);
+    const bool liftable = !s.hdr->status && s.M;
+    g.sync();
+    if (liftable) lift_shot(s, g, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
+    else if (g.tid == 0 && p.edge_dump_len) *p.edge_dump_len = 0;
+    g.sync();
     if (g.tid == 0) {
-        uint64_t obs = 0;
-        if (!s.hdr->status && s.M) lift_shot(s, &obs, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
-        else if (p.edge_dump_len) *p.edge_dump_len = 0;
         pt.lap(6);
         if (p.phase_cycles) {
             for (int k = 0; k < 7; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[k], pt.t[k]);
@@ -1436,7 +1576,7 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
         }
         uint32_t st = s.hdr->status;
         p.status_out[shot] = st;
-        p.obs_out[shot] = st ? 0 : obs;
+        p.obs_out[shot] = st ? 0 : s.hdr->obs;
         if (p.weight_out) p.weight_out[shot] = st ? 0 : (int64_t)s.hdr->weight;
         if (p.rounds_out) p.rounds_out[shot] = rounds;
     }

@@ -59,7 +59,7 @@ void cbsim_graph_export(void *h, uint32_t *row_ptr, uint32_t *nbr, int32_t *wt) 
 // Decodes shots one by one. Returns 0. status_out[k] != 0 marks failed shots.
 // edges_out (nullable): matched edges of the LAST shot (interleaved), *num_edge_ints receives the count.
 int cbsim_decode(void *h, const uint8_t *dets, uint64_t num_shots, uint64_t stride, uint64_t *obs_out, int64_t *weight_out,
-                 uint32_t *status_out, uint32_t *rounds_out, uint32_t ht_log2, uint64_t dyn_bytes, int64_t *edges_out,
+                 uint32_t *status_out, uint32_t *rounds_out, uint32_t ht_log2, uint32_t sh_ht_log2, uint64_t dyn_bytes, int64_t *edges_out,
                  uint64_t edges_cap, uint64_t *num_edge_ints) {
     auto *s = (Sim *)h;
     DecodeParams p{};
@@ -74,19 +74,22 @@ int cbsim_decode(void *h, const uint8_t *dets, uint64_t num_shots, uint64_t stri
     p.edge_dump = edges_out;
     p.edge_dump_cap = edges_cap;
     p.edge_dump_len = num_edge_ints;
+    p.cfg.sh_ht_log2 = sh_ht_log2;
+    p.cfg.sh_found = 8;
     p.cfg.ht_log2 = ht_log2;
-    p.cfg.heap_cap = 2u << ht_log2;
     p.cfg.found_cap = 256;
     p.cfg.max_events = 2 * s->tables.num_dets + 2;
     p.cfg.dyn_bytes = dyn_bytes;
     uint64_t bytes = arena_bytes_per_group(p.cfg, p.T.num_nodes, 1);
     s->arena.assign(bytes, 0);
+    std::vector<uint8_t> shared(shared_bytes_per_group(p.cfg, p.T.num_dets, 1) + 16, 0);
     p.arena = s->arena.data();
     p.arena_stride = bytes;
     HostGroup g;
     Shot shot;
-    bind_shot(shot, p, p.arena, g);
+    bind_shot(shot, p, p.arena, shared.data(), g);
     init_group_arena(shot, g);
+    init_group_shared(shot, g);
     for (uint32_t k = 0; k < num_shots; k++) decode_shot(shot, p, k, g);
     return 0;
 }

@@ -28,7 +28,7 @@ def lib():
             getattr(L, n).argtypes = [vp]
         L.cbsim_free_string.argtypes = [vp]
         L.cbsim_graph_export.argtypes = [vp, vp, vp, vp]
-        L.cbsim_decode.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, ctypes.c_uint32, u64, vp, u64, vp]
+        L.cbsim_decode.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, u64, vp, u64, vp]
         _lib = L
     return _lib
 
@@ -76,7 +76,7 @@ class SimDecoder:
         L.cbsim_graph_export(self._h, _p(row_ptr), _p(nbr), _p(wt))
         return row_ptr, nbr, wt
 
-    def decode(self, dets, ht_log2=12, dyn_bytes=64 << 20, want_edges=False):
+    def decode(self, dets, ht_log2=12, dyn_bytes=64 << 20, want_edges=False, sh_ht_log2=5):
         dets = np.ascontiguousarray(dets, dtype=np.uint8)
         if dets.ndim == 1:
             dets = dets[None, :]
@@ -87,7 +87,7 @@ class SimDecoder:
         rd = np.zeros(n, np.uint32)
         edges = np.zeros(1 << 16, np.int64) if want_edges else None
         ne = ctypes.c_uint64(0)
-        lib().cbsim_decode(self._h, _p(dets), n, dets.shape[1], _p(obs), _p(w), _p(st), _p(rd), ht_log2, dyn_bytes,
+        lib().cbsim_decode(self._h, _p(dets), n, dets.shape[1], _p(obs), _p(w), _p(st), _p(rd), ht_log2, sh_ht_log2, dyn_bytes,
                            _p(edges) if want_edges else None, len(edges) if want_edges else 0,
                            ctypes.byref(ne) if want_edges else None)
         if want_edges:

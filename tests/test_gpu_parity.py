@@ -36,15 +36,13 @@ def libs(built):
     return chromobius_b200, oracle
 
 
-@pytest.mark.parametrize('group', [32, 128, 1])
+@pytest.mark.parametrize('group', [32, 128, 256])
 @pytest.mark.parametrize('name,shots,seed', CASES)
 def test_batch_matches_oracle(libs, name, shots, seed, group):
     cb, oracle = libs
     text = read_dem(name)
     dec = cb._compile_text(text, device=0)
     dec.set_tuning(group_threads=group)
-    if group == 1:
-        shots = min(shots, 1000)
     dets, _ = NumpyDemSampler(text).sample(shots, seed)
     pred, wint = dec.decode_with_integer_weights(dets)
     o_obs, o_w = oracle.OracleDecoder(text).decode_batch(dets)

@@ -39,3 +39,10 @@ if check:
     n = min(shots, int(sys.argv[5]) if len(sys.argv) > 5 else 500)
     oo, ow = oracle.OracleDecoder(text).decode_batch(dets[:n])
     print('  oracle check on %d shots: weight diffs %d obs diffs %d' % (n, (ow != ref[1][:n]).sum(), (oo != m[:n]).sum()))
+# phase profile of the first group width
+dec.set_tuning(group_threads=groups[0])
+dec.profile_phases(True)
+dec.decode_with_integer_weights(dets)
+ph = dec.profile_phases(False)
+tot = sum(v for k, v in ph.items() if k != 'shots')
+print('  phases (cycles/shot of thread 0, group=%d): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k != 'shots'))
