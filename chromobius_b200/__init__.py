@@ -94,6 +94,8 @@ def load_library():
     L.cb200_decode_shot_edges.argtypes = [vp, vp, vp, u64, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(i64)]
     L.cb200_set_tuning.restype = ctypes.c_int
     L.cb200_set_tuning.argtypes = [vp, u32, u32]
+    L.cb200_set_groups_per_sm.restype = ctypes.c_int
+    L.cb200_set_groups_per_sm.argtypes = [vp, u32]
     L.cb200_profile_phases.restype = ctypes.c_int
     L.cb200_profile_phases.argtypes = [vp, ctypes.c_int, vp]
     L.cb200_sampler_last_error.restype = ctypes.c_char_p
@@ -262,9 +264,10 @@ class CompiledDecoder:
                 return edges[:need.value].reshape(-1, 2), int(obs.value), int(w.value)
             cap = int(need.value)
 
-    def set_tuning(self, group_threads=0, ht_log2=0):
+    def set_tuning(self, group_threads=0, ht_log2=0, groups_per_sm=0):
         if self._L.cb200_set_tuning(self._h, group_threads, ht_log2) != 0:
             _raise_last(self._L)
+        self._L.cb200_set_groups_per_sm(self._h, groups_per_sm)
 
     def profile_phases(self, enable=True):
         """Enables phase profiling for later calls; returns the cycle counters of the last profiled call as a dict."""

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict_
 
 // K2: the decode kernel. Persistent groups pull shots from a queue.
 template <int GROUP>
-__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP)
+__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? 3 : 6))
     k_decode(DecodeParams p, uint32_t num_groups, uint32_t smem_per_group) {
     uint32_t group, gib;
     DevGroup<GROUP> g;
@@ -205,12 +205,10 @@ struct cb200_decoder {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
-    // device tables
-    DeviceBuf<uint32_t> d_row_ptr, d_adj_drag, d_self_drag;
-    DeviceBuf<AdjEntry> d_adj;
-    DeviceBuf<uint8_t> d_det_info, d_ingest_mask;
-    DeviceBuf<uint64_t> d_rep_obs;
-    DeviceBuf<DragEntry> d_drag;
+    // device tables (one allocation, see upload_tables)
+    DeviceBuf<uint8_t> d_tables;
+    size_t l2_window_bytes = 0;
+    uint32_t tune_groups_per_sm = 0;
     TablesView dview{};
     uint64_t table_bytes = 0;
     // per-call buffers (grow only)
@@ -232,31 +230,70 @@ struct cb200_decoder {
 
 namespace {
 
+// All read-only tables live in ONE allocation so that a single L2 access-policy window can pin them: the matcher
+// graph is re-read by every ball of every shot, while the per-shot scratch streams through L2 behind it.
 void upload_tables(cb200_decoder *d) {
     const HostTables &h = d->host;
-    auto up = [&](auto &buf, const auto &vec) {
-        buf.ensure(vec.size());
-        if (!vec.empty()) CUDA_CHECK(cudaMemcpy(buf.ptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
-        d->table_bytes += vec.size() * sizeof(vec[0]);
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t off = total;
+        total += (bytes + 255) & ~size_t{255};
+        return off;
     };
-    up(d->d_row_ptr, h.row_ptr);
-    up(d->d_adj, h.adj);
-    up(d->d_adj_drag, h.adj_drag);
-    up(d->d_det_info, h.det_info);
-    up(d->d_rep_obs, h.rep_obs);
-    up(d->d_self_drag, h.self_drag);
-    up(d->d_ingest_mask, h.ingest_mask);
-    up(d->d_drag, h.drag);
+    // hot first: the window covers a prefix if the set-aside is smaller than the tables
+    size_t o_ell = reserve(h.ell_adj.size() * sizeof(AdjEntry));
+    size_t o_row = reserve(h.row_ptr.size() * 4);
+    size_t o_adj = reserve(h.adj.size() * sizeof(AdjEntry));
+    size_t o_mask = reserve(h.ingest_mask.size());
+    size_t o_info = reserve(h.det_info.size());
+    size_t o_rep = reserve(h.rep_obs.size() * 8);
+    size_t o_self = reserve(h.self_drag.size() * 4);
+    size_t o_adrag = reserve(h.adj_drag.size() * 4);
+    size_t o_drag = reserve(h.drag.size() * sizeof(DragEntry));
+    d->d_tables.ensure(total + 256);
+    uint8_t *base = d->d_tables.ptr;
+    auto put = [&](size_t off, const void *src, size_t bytes) {
+        if (bytes) CUDA_CHECK(cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice));
+    };
+    put(o_ell, h.ell_adj.data(), h.ell_adj.size() * sizeof(AdjEntry));
+    put(o_row, h.row_ptr.data(), h.row_ptr.size() * 4);
+    put(o_adj, h.adj.data(), h.adj.size() * sizeof(AdjEntry));
+    put(o_mask, h.ingest_mask.data(), h.ingest_mask.size());
+    put(o_info, h.det_info.data(), h.det_info.size());
+    put(o_rep, h.rep_obs.data(), h.rep_obs.size() * 8);
+    put(o_self, h.self_drag.data(), h.self_drag.size() * 4);
+    put(o_adrag, h.adj_drag.data(), h.adj_drag.size() * 4);
+    put(o_drag, h.drag.data(), h.drag.size() * sizeof(DragEntry));
+    d->table_bytes = total;
     TablesView v = h.view();
-    v.row_ptr = d->d_row_ptr.ptr;
-    v.adj = d->d_adj.ptr;
-    v.adj_drag = d->d_adj_drag.ptr;
-    v.det_info = d->d_det_info.ptr;
-    v.rep_obs = d->d_rep_obs.ptr;
-    v.self_drag = d->d_self_drag.ptr;
-    v.ingest_mask = d->d_ingest_mask.ptr;
-    v.drag = d->d_drag.ptr;
+    v.ell_adj = (const AdjEntry *)(base + o_ell);
+    v.row_ptr = (const uint32_t *)(base + o_row);
+    v.adj = (const AdjEntry *)(base + o_adj);
+    v.ingest_mask = base + o_mask;
+    v.det_info = base + o_info;
+    v.rep_obs = (const uint64_t *)(base + o_rep);
+    v.self_drag = (const uint32_t *)(base + o_self);
+    v.adj_drag = (const uint32_t *)(base + o_adrag);
+    v.drag = (const DragEntry *)(base + o_drag);
     d->dview = v;
+    // L2 persistence for the tables (best effort: older drivers / MIG slices may refuse).
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, d->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, d->device);
+    if (max_persist > 0 && max_window > 0 && total > 0) {
+        size_t want = std::min<size_t>(total, (size_t)max_persist);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = base;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(total, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(d->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                d->l2_window_bytes = attr.accessPolicyWindow.num_bytes;
+        }
+        cudaGetLastError();
+    }
 }
 
 template <int GROUP>
@@ -319,11 +356,11 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     Plan pl{};
     uint32_t group = d->tune_group;
     if (group == 0) group = mean_det_events >= 24 ? 128 : 32;
-    if (group != 32 && group != 128 && group != 256) group = 32;
+    if (group != 32 && group != 128 && group != 256 && group != 512) group = 32;
     pl.group = group;
     uint32_t full = 4;
     while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
-    uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 9;
+    uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 8;
     uint32_t gl = std::min<uint32_t>(full, 13 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
     pl.cfg.sh_found = 24;
@@ -333,16 +370,23 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     pl.cfg.dyn_bytes = ((uint64_t)(64 << 10) + (uint64_t)3072 * pl.cfg.max_events) << (3 * escalation);
     uint32_t nwarps = group == 32 ? 1 : group / 32;
     pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
-    int per_sm = group == 32 ? blocks_per_sm<32>(pl.smem_per_group) * (WARP_MODE_BLOCK / 32)
-                             : (group == 128 ? blocks_per_sm<128>(pl.smem_per_group) : blocks_per_sm<256>(pl.smem_per_group));
+    auto occupancy = [&](uint32_t smem) {
+        switch (group) {
+            case 32: return blocks_per_sm<32>(smem) * (WARP_MODE_BLOCK / 32);
+            case 128: return blocks_per_sm<128>(smem);
+            case 256: return blocks_per_sm<256>(smem);
+            default: return blocks_per_sm<512>(smem);
+        }
+    };
+    int per_sm = occupancy(pl.smem_per_group);
     if (per_sm <= 0) {
         // the row does not fit beside the ball tables: drop the shared tables, keep the row
         pl.cfg.sh_ht_log2 = 0;
         pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
-        per_sm = group == 32 ? blocks_per_sm<32>(pl.smem_per_group) * (WARP_MODE_BLOCK / 32)
-                             : (group == 128 ? blocks_per_sm<128>(pl.smem_per_group) : blocks_per_sm<256>(pl.smem_per_group));
+        per_sm = occupancy(pl.smem_per_group);
         if (per_sm <= 0) throw std::invalid_argument("detector error model too large: one shot's row does not fit in shared memory");
     }
+    if (d->tune_groups_per_sm && (int)d->tune_groups_per_sm < per_sm) per_sm = (int)d->tune_groups_per_sm;
     uint64_t want = (uint64_t)d->num_sms * (uint32_t)per_sm;
     pl.groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, work_items));
     return pl;
@@ -360,7 +404,8 @@ void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &l
         p.arena = d->d_arena.ptr;
         if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
         else if (pl.group == 128) launch_init<128>(p, pl.groups, d->stream);
-        else launch_init<256>(p, pl.groups, d->stream);
+        else if (pl.group == 256) launch_init<256>(p, pl.groups, d->stream);
+        else launch_init<512>(p, pl.groups, d->stream);
         CUDA_CHECK(cudaGetLastError());
         launches++;
         d->arena_group = pl.group;
@@ -469,7 +514,8 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         }
         if (pl.group == 32) launch_decode<32>(p, pl.groups, pl.smem_per_group, s);
         else if (pl.group == 128) launch_decode<128>(p, pl.groups, pl.smem_per_group, s);
-        else launch_decode<256>(p, pl.groups, pl.smem_per_group, s);
+        else if (pl.group == 256) launch_decode<256>(p, pl.groups, pl.smem_per_group, s);
+        else launch_decode<512>(p, pl.groups, pl.smem_per_group, s);
         CUDA_CHECK(cudaGetLastError());
         launches++;
         if (esc == 0) CUDA_CHECK(cudaEventRecord(d->ev[3], s));
@@ -606,8 +652,7 @@ void cb200_free(cb200_decoder *d) {
         cudaSetDevice(d->device);
         cudaStreamSynchronize(d->stream);
     }
-    d->d_row_ptr.release(); d->d_adj_drag.release(); d->d_self_drag.release(); d->d_adj.release();
-    d->d_det_info.release(); d->d_ingest_mask.release(); d->d_rep_obs.release(); d->d_drag.release();
+    d->d_tables.release();
     d->d_dets.release(); d->d_obs_bytes.release(); d->d_arena.release(); d->d_obs64.release(); d->d_wint.release();
     d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();
     d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release(); d->d_phase.release();
@@ -634,8 +679,8 @@ char *cb200_describe(const cb200_decoder *d) {
 void cb200_free_string(char *s) { free(s); }
 
 int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2) {
-    if (group_threads != 0 && group_threads != 32 && group_threads != 128 && group_threads != 256) {
-        g_error = "group_threads must be 0, 32, 128 or 256";
+    if (group_threads != 0 && group_threads != 32 && group_threads != 128 && group_threads != 256 && group_threads != 512) {
+        g_error = "group_threads must be 0, 32, 128, 256 or 512";
         return CB200_ERR_INVALID_ARGUMENT;
     }
     if (ht_log2 != 0 && (ht_log2 < 4 || ht_log2 > 24)) {
@@ -644,6 +689,12 @@ int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2)
     }
     d->tune_group = group_threads;
     d->tune_ht_log2 = ht_log2;
+    return CB200_OK;
+}
+
+int cb200_set_groups_per_sm(cb200_decoder *d, uint32_t groups_per_sm) {
+    if (!d) return CB200_ERR_INVALID_ARGUMENT;
+    d->tune_groups_per_sm = groups_per_sm;
     return CB200_OK;
 }
 

@@ -191,7 +191,8 @@ struct GroupHeader {
     uint32_t bcast;
     uint32_t lift_ncomp;
     uint32_t lift_cyc_top;
-    uint32_t pad[2];
+    uint32_t nbig;
+    uint32_t pad[1];
 };
 
 // Ball tables of one warp: open-addressing hash (node -> distance, frontier position) plus the frontier itself.
@@ -200,26 +201,31 @@ struct BallTables {
     int64_t *dist;     // [H]
     uint32_t *fpos;    // [H] position in `front`, FRONT_CLOSED once settled
     uint32_t *used;    // [cap] slots in insertion order (O(touched) clean-up)
-    uint32_t *front;   // [cap] slots of the open nodes
+    uint64_t *front;   // [cap] open nodes as (distance << 20 | slot): the minimum is the next node to settle
     NbEntry *found;    // [fcap]
     uint32_t H, cap, fcap;
     uint32_t nused, nfront;
+    uint8_t *raw;      // start of the region (reused as blossom scratch between ball phases)
+    uint64_t raw_bytes;
 };
 
 CB_HD uint64_t ball_table_bytes(uint32_t log2, uint32_t fcap) {
     if (log2 == 0) return 0;
     uint64_t H = uint64_t{1} << log2;
     uint64_t cap = H * 3 / 4;
-    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(cap * 4) * 2 + align16(uint64_t{fcap} * sizeof(NbEntry));
+    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(cap * 4) + align16(cap * 8) +
+           align16(uint64_t{fcap} * sizeof(NbEntry));
 }
 CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t fcap) {
     uint64_t H = uint64_t{1} << log2;
     uint64_t cap = H * 3 / 4;
+    t.raw = p;
+    t.raw_bytes = ball_table_bytes(log2, fcap);
     t.key = (uint32_t *)p; p += align16(H * 4);
     t.dist = (int64_t *)p; p += align16(H * 8);
     t.fpos = (uint32_t *)p; p += align16(H * 4);
     t.used = (uint32_t *)p; p += align16(cap * 4);
-    t.front = (uint32_t *)p; p += align16(cap * 4);
+    t.front = (uint64_t *)p; p += align16(cap * 8);
     t.found = (NbEntry *)p;
     t.H = log2 ? (uint32_t)H : 0;
     t.cap = (uint32_t)cap;
@@ -447,15 +453,36 @@ CB_HD void ball_clear(BallTables &t, const G &g) {
 
 enum BallResult : int { BALL_OK = 0, BALL_OVERFLOW = 1, BALL_EXHAUSTED = 2 };
 
+// Adjacency row of a node: fixed-stride (ELL) rows when the graph's maximum degree allows, CSR otherwise.
+struct RowRange {
+    uint32_t e0, e1;
+};
+CB_HD RowRange row_of(const TablesView &T, uint32_t u) {
+    RowRange r;
+    if (T.ell_shift) {
+        r.e0 = u << T.ell_shift;
+        r.e1 = r.e0 + (1u << T.ell_shift);
+    } else {
+        r.e0 = T.row_ptr[u];
+        r.e1 = T.row_ptr[u + 1];
+    }
+    return r;
+}
+CB_HD const AdjEntry *adj_of(const TablesView &T) { return T.ell_shift ? T.ell_adj : T.adj; }
+
 // Grows a ball around `src` (all lanes of the warp call this together; every lane returns the same values).
-//   radius >= 0 : settle every node within `radius`
-//   radius <  0 : grow until more than `need_more_than` events have been seen, then finish that distance level
-//   stop_node   : stop as soon as this node is settled (NO_INDEX: never)
-// Other events settled inside the ball are appended to t.found. The tables are left populated (caller clears).
+// Nodes are settled in order of distance.
+//   radius <  0 : stop as soon as more than `need_more_than` other events have been settled; *limit_out = distance of
+//                 the last one. Every event strictly closer than *limit_out has been reported.
+//   radius >= 0, !inclusive : settle every node strictly closer than `radius`; *limit_out = radius.
+//   radius >= 0,  inclusive : settle every node within `radius`, stopping early when `stop_node` is settled.
+// Other events settled inside the ball are appended to t.found when collect_events is set.
+// The tables are left populated (the caller clears them).
 template <class G>
 CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int64_t radius, uint32_t need_more_than,
-                    uint32_t stop_node, bool collect_events, int64_t *limit_out, uint32_t *nfound_out) {
+                    uint32_t stop_node, bool collect_events, bool inclusive, int64_t *limit_out, uint32_t *nfound_out) {
     const uint32_t hmask = t.H - 1;
+    const AdjEntry *adj = adj_of(s.T);
     if (g.lane == 0) {
         uint32_t k = ht_hash(src, t.H);
         t.key[k] = src;
@@ -474,20 +501,20 @@ CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int6
         // pop the closest open node
         uint64_t best = ~uint64_t{0};
         for (uint32_t q = g.lane; q < t.nfront; q += g.lanes) {
-            uint64_t cand = ((uint64_t)t.dist[t.front[q]] << 20) | q;
+            uint64_t cand = t.front[q];
             best = cand < best ? cand : best;
         }
         best = g.min64(best);
         const int64_t d = (int64_t)(best >> 20);
-        const uint32_t q = (uint32_t)(best & 0xFFFFF);
-        if (limit >= 0 && d > limit) break;
-        const uint32_t slot = t.front[q];
+        const uint32_t slot = (uint32_t)(best & 0xFFFFF);
+        if (limit >= 0 && (inclusive ? d > limit : d >= limit)) break;
         const uint32_t u = t.key[slot];
+        const uint32_t q = t.fpos[slot];
         g.wsync();
         if (g.lane == 0) {
-            uint32_t last = t.front[t.nfront - 1];
+            uint64_t last = t.front[t.nfront - 1];
             t.front[q] = last;
-            t.fpos[last] = q;
+            t.fpos[(uint32_t)(last & 0xFFFFF)] = q;
             t.fpos[slot] = FRONT_CLOSED;
         }
         t.nfront--;
@@ -504,21 +531,25 @@ CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int6
                 t.found[nfound].d = d;
             }
             nfound++;
-            if (limit < 0 && nfound > need_more_than) limit = d;
+            if (limit < 0 && nfound > need_more_than) {
+                limit = d;
+                break;
+            }
         }
-        const uint32_t e0 = s.T.row_ptr[u], e1 = s.T.row_ptr[u + 1];
-        if (t.nused + (e1 - e0) > t.cap || t.nused + (e1 - e0) >= (1u << 20)) {
+        const RowRange row = row_of(s.T, u);
+        if (t.nused + (row.e1 - row.e0) > t.cap) {
             result = BALL_OVERFLOW;
             break;
         }
-        for (uint32_t base = e0; base < e1; base += g.lanes) {
+        for (uint32_t base = row.e0; base < row.e1; base += g.lanes) {
             const uint32_t e = base + g.lane;
             bool is_new = false;
             uint32_t my_slot = 0;
-            if (e < e1) {
-                AdjEntry a = s.T.adj[e];
-                int64_t nd = d + a.wt;
-                if (!(limit >= 0 && nd > limit)) {
+            int64_t nd = 0;
+            if (e < row.e1) {
+                AdjEntry a = adj[e];
+                nd = d + a.wt;
+                if (a.nbr != NO_INDEX && !(limit >= 0 && (inclusive ? nd > limit : nd >= limit))) {
                     uint32_t k = ht_hash(a.nbr, t.H);
                     while (true) {
                         uint32_t old = cb_atomic_cas(&t.key[k], HT_EMPTY, a.nbr);
@@ -530,15 +561,22 @@ CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int6
                         k = (k + 1) & hmask;
                     }
                     my_slot = k;
-                    if (is_new) t.dist[k] = nd;
-                    else if (t.fpos[k] != FRONT_CLOSED && nd < t.dist[k]) t.dist[k] = nd;
+                    if (is_new) {
+                        t.dist[k] = nd;
+                    } else {
+                        uint32_t fp = t.fpos[k];
+                        if (fp != FRONT_CLOSED && nd < t.dist[k]) {
+                            t.dist[k] = nd;
+                            t.front[fp] = ((uint64_t)nd << 20) | k;
+                        }
+                    }
                 }
             }
             const uint32_t fresh = g.ballot(is_new);
             if (is_new) {
                 uint32_t idx = popc32(fresh & ((1u << g.lane) - 1));
                 t.used[t.nused + idx] = my_slot;
-                t.front[t.nfront + idx] = my_slot;
+                t.front[t.nfront + idx] = ((uint64_t)nd << 20) | my_slot;
                 t.fpos[my_slot] = t.nfront + idx;
             }
             const uint32_t c = popc32(fresh);
@@ -562,11 +600,11 @@ CB_HD void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32
     int64_t limit = 0;
     uint32_t nfound = 0;
     BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
-    int r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, &limit, &nfound);
+    int r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, false, &limit, &nfound);
     if (r == BALL_OVERFLOW && t == &s.sh_ball) {
         ball_clear(*t, g);
         t = &s.gl_ball;
-        r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, &limit, &nfound);
+        r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, false, &limit, &nfound);
     }
     ball_clear(*t, g);
     if (r == BALL_OVERFLOW) {
@@ -997,8 +1035,9 @@ CB_HD void request_growth(Shot &s, uint32_t ev, int64_t to) {
     s.grow_to[k] = to;
 }
 
-// Solves component c (members sorted ascending). Either commits partners or requests growth.
-CB_HD void solve_component(Shot &s, uint32_t c) {
+// First pass over component c, one thread per component: sorts the members, handles odd components (everyone grows)
+// and single-edge components (closed form). Returns false when the component needs the blossom solver.
+CB_HD bool solve_component_small(Shot &s, uint32_t c) {
     uint32_t r = s.comp_root[c];
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
@@ -1014,7 +1053,7 @@ CB_HD void solve_component(Shot &s, uint32_t c) {
     }
     if (n & 1) {
         for (uint32_t a = 0; a < n; a++) request_growth(s, mem[a], -1);
-        return;
+        return true;
     }
     if (n == 2) {
         // Closed form of the blossom on one edge: y = d/2 each, so both balls need radius >= d.
@@ -1027,13 +1066,23 @@ CB_HD void solve_component(Shot &s, uint32_t c) {
             s.partner[i] = (int32_t)j;
             s.partner[j] = (int32_t)i;
         }
-        return;
+        return true;
     }
+    return false;
+}
+
+// Exact solve of component c by the dense blossom, on one thread. `scratch` (nullable) is fast memory the solver may
+// use when the component fits; otherwise the scratch comes from the dynamic region.
+CB_HD void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
+    uint32_t r = s.comp_root[c];
+    uint32_t n = s.cnt[r];
+    uint32_t *mem = s.members + s.start[r];
     if (n > MAX_COMPONENT) {
         s.fail(SHOT_COMPONENT_TOO_LARGE);
         return;
     }
-    uint8_t *memory = s.alloc(Blossom::bytes_needed((int)n));
+    uint64_t need_bytes = Blossom::bytes_needed((int)n);
+    uint8_t *memory = (scratch && need_bytes <= scratch_bytes) ? scratch : s.alloc(need_bytes);
     if (!memory) return;
     Blossom bl;
     bl.bind(memory, (int)n);
@@ -1105,6 +1154,7 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             s.hdr->ncomp = 0;
             s.hdr->mem_top = 0;
             s.hdr->ngrow = 0;
+            s.hdr->nbig = 0;
         }
         g.sync();
         for (uint32_t i = g.tid; i < M; i += g.n) {
@@ -1140,7 +1190,21 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         g.sync();
         const uint32_t ncomp = s.hdr->ncomp;
         pt.lap(2);
-        for (uint32_t c = g.tid; c < ncomp; c += g.n) solve_component(s, c);
+        // small components: one thread each; the rest is queued for the blossom (s.root is free again: queue)
+        for (uint32_t c = g.tid; c < ncomp; c += g.n)
+            if (!solve_component_small(s, c)) s.root[cb_atomic_add(&s.hdr->nbig, 1)] = c;
+        g.sync();
+        const uint32_t nbig = s.hdr->nbig;
+        // blossom components: one warp each, solved by lane 0 inside the warp's shared-memory ball tables
+        bool used_shared = false;
+        for (uint32_t k = g.warp; k < nbig; k += g.nwarps) {
+            if (g.lane == 0) solve_component_blossom(s, s.root[k], s.sh_ball.H ? s.sh_ball.raw : nullptr, s.sh_ball.raw_bytes);
+            used_shared = true;
+        }
+        if (used_shared && s.sh_ball.H) {
+            g.wsync();
+            for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
+        }
         g.sync();
         pt.lap(3);
         const uint32_t st = s.hdr->status;
@@ -1166,11 +1230,11 @@ CB_HD void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_t
     int64_t limit = 0;
     uint32_t nfound = 0;
     BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
-    int r = ball_grow(s, g, *t, src, d_total, 0, dst, false, &limit, &nfound);
+    int r = ball_grow(s, g, *t, src, d_total, 0, dst, false, true, &limit, &nfound);
     if (r == BALL_OVERFLOW && t == &s.sh_ball) {
         ball_clear(*t, g);
         t = &s.gl_ball;
-        r = ball_grow(s, g, *t, src, d_total, 0, dst, false, &limit, &nfound);
+        r = ball_grow(s, g, *t, src, d_total, 0, dst, false, true, &limit, &nfound);
     }
     bool ok = r == BALL_OK;
     uint32_t len = 1;
@@ -1184,19 +1248,22 @@ CB_HD void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_t
         pos--;
         uint32_t steps = 0;
         while (cur != src) {
-            const uint32_t e0 = s.T.row_ptr[cur], e1 = s.T.row_ptr[cur + 1];
+            const RowRange row = row_of(s.T, cur);
+            const AdjEntry *adj = adj_of(s.T);
             uint32_t best = NO_INDEX;
             int64_t bd = 0;
-            for (uint32_t base = e0; base < e1 && best == NO_INDEX; base += g.lanes) {
+            for (uint32_t base = row.e0; base < row.e1 && best == NO_INDEX; base += g.lanes) {
                 uint32_t e = base + g.lane;
                 bool hit = false;
                 int64_t dv = -1;
                 uint32_t nbr = 0;
-                if (e < e1) {
-                    AdjEntry a = s.T.adj[e];
+                if (e < row.e1) {
+                    AdjEntry a = adj[e];
                     nbr = a.nbr;
-                    dv = ball_lookup(*t, nbr);
-                    hit = dv >= 0 && dv + a.wt == dc;
+                    if (nbr != NO_INDEX) {
+                        dv = ball_lookup(*t, nbr);
+                        hit = dv >= 0 && dv + a.wt == dc;
+                    }
                 }
                 uint32_t hits = g.ballot(hit);
                 if (hits) {

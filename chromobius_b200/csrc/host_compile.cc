@@ -891,6 +891,22 @@ HostTables compile_tables(const FlatDem &dem) {
     pass_matching_graph(cx);
     pass_drag(cx, order, obs);
 
+    // Fixed-stride adjacency rows: one aligned row per node, so a warp fetches a row with a single request and the
+    // row_ptr indirection disappears from the ball-growth loop.
+    {
+        uint32_t max_deg = 0;
+        for (uint32_t u = 0; u + 1 < t.row_ptr.size(); u++) max_deg = std::max(max_deg, t.row_ptr[u + 1] - t.row_ptr[u]);
+        t.ell_shift = 0;
+        if (max_deg >= 1 && max_deg <= 32) {
+            uint32_t sh = 1;
+            while ((1u << sh) < max_deg) sh++;
+            t.ell_shift = sh;
+            t.ell_adj.assign((size_t)(t.num_dets * 2) << sh, AdjEntry{NO_INDEX, 0});
+            for (uint32_t u = 0; u + 1 < t.row_ptr.size(); u++)
+                for (uint32_t k = t.row_ptr[u]; k < t.row_ptr[u + 1]; k++)
+                    t.ell_adj[((size_t)u << sh) + (k - t.row_ptr[u])] = t.adj[k];
+        }
+    }
     t.det_info.assign(t.num_dets, 0);
     t.rep_obs.assign(t.num_dets, 0);
     t.ingest_mask.assign((t.num_dets + 7) / 8, 0);
@@ -913,6 +929,8 @@ TablesView HostTables::view() const {
     v.num_det_bytes = (num_dets + 7) / 8;
     v.row_ptr = row_ptr.data();
     v.adj = adj.data();
+    v.ell_adj = ell_adj.data();
+    v.ell_shift = ell_shift;
     v.adj_drag = adj_drag.data();
     v.det_info = det_info.data();
     v.rep_obs = rep_obs.data();

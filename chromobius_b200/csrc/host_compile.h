@@ -71,6 +71,8 @@ struct HostTables {
     // Device-shaped tables.
     std::vector<uint32_t> row_ptr;
     std::vector<AdjEntry> adj;
+    std::vector<AdjEntry> ell_adj;   // fixed-stride copy of adj (1 << ell_shift entries per node), see TablesView
+    uint32_t ell_shift = 0;
     std::vector<uint32_t> adj_drag;
     std::vector<uint8_t> det_info;
     std::vector<uint64_t> rep_obs;

@@ -45,6 +45,8 @@ struct TablesView {
     uint32_t num_det_bytes;   // ceil(num_dets / 8)
     const uint32_t *row_ptr;  // [num_nodes + 1]
     const AdjEntry *adj;      // [row_ptr[num_nodes]] sorted by nbr within a row
+    const AdjEntry *ell_adj;  // [num_nodes << ell_shift] the same rows at a fixed stride, padded with nbr == NO_INDEX
+    uint32_t ell_shift;       // 0: no fixed-stride copy (maximum degree above 32)
     const uint32_t *adj_drag; // [row_ptr[num_nodes]] DragEntry index of the detector pair of this half-edge
     const uint8_t *det_info;  // [num_dets]
     const uint64_t *rep_obs;  // [num_dets] rgb_reps[d].obs_flip

@@ -1277,9 +1277,9 @@ struct Decoder {
         return true;
     }
 
-    // Ball around one event (truncated Dijkstra). radius >= 0: everything within radius. radius < 0: until more than
-    // `need_more_than` other events are inside, then the whole distance level is finished. Returns the radius reached
-    // (-1 when nothing more is reachable).
+    // Open ball around one event (truncated Dijkstra). radius >= 0: every node strictly closer than radius. radius < 0:
+    // until more than `need_more_than` other events have been settled; the radius is the distance of the last one, and
+    // every event strictly closer than it has been reported. Returns the radius (-1 when nothing more is reachable).
     int64_t ball(node_t src, int64_t radius, size_t need_more_than, std::vector<std::pair<int, int64_t>> *found) {
         ReusableHeap &pq = heap_buf;
         pq.clear();
@@ -1293,15 +1293,18 @@ struct Decoder {
             auto [d, u] = pq.top();
             pq.pop();
             if (d != dist[u]) continue;
-            if (limit >= 0 && d > limit) break;
+            if (limit >= 0 && d >= limit) break;  // open ball: every event strictly closer than the radius is known
             if (u != src && event_index[u] >= 0) {
                 found->push_back({event_index[u], d});
-                if (limit < 0 && found->size() > need_more_than) limit = d;
+                if (limit < 0 && found->size() > need_more_than) {
+                    limit = d;
+                    break;
+                }
             }
             for (uint32_t k = t->row_ptr[u]; k < t->row_ptr[u + 1]; k++) {
                 node_t v = t->nbr[k];
                 int64_t nd = d + t->wt[k];
-                if (limit >= 0 && nd > limit) continue;
+                if (limit >= 0 && nd >= limit) continue;
                 if (dist[v] < 0 || nd < dist[v]) {
                     if (dist[v] < 0) touched.push_back(v);
                     dist[v] = nd;

@@ -7,7 +7,7 @@ import chromobius_b200 as cb
 from dem_util import read_dem
 from synth import FastDemSampler
 
-name = sys.argv[1]; shots = int(sys.argv[2]); groups = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [32, 128]
+name = sys.argv[1]; shots = int(sys.argv[2]); groups = [x for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else ['32', '128']
 check = len(sys.argv) > 4 and sys.argv[4] == 'check'
 text = read_dem(name)
 t0 = time.time(); dec = cb._compile_text(text, device=0); t1 = time.time()
@@ -16,15 +16,19 @@ dets, obs = smp.sample(shots, 0)
 t2 = time.time()
 print('%s: compile %.2fs sample %.2fs D=%d table_bytes=%d' % (name, t1 - t0, t2 - t1, dec.num_detectors, dec.table_bytes), flush=True)
 ref = None
-for g in groups:
-    dec.set_tuning(group_threads=g)
+def tune(spec):
+    parts = str(spec).split(':')
+    dec.set_tuning(group_threads=int(parts[0]), groups_per_sm=int(parts[1]) if len(parts) > 1 else 0)
+    return int(parts[0])
+for gspec in groups:
+    g = tune(gspec)
     for rep in range(2):
         t0 = time.time()
         pred, wint = dec.decode_with_integer_weights(dets)
         dt = time.time() - t0
         st = dec.last_stats
-        print('  group=%3d rep%d wall %.3fs  decode %.2f ms (%.2f us/shot, %.0f shots/s) count %.3f ms h2d %.2f ms events/shot %.1f rounds/shot %.2f retried %d groups %d' % (
-            g, rep, dt, st.ms_decode, st.ms_decode * 1e3 / shots, shots / (st.ms_decode * 1e-3), st.ms_count, st.ms_h2d,
+        print('  group=%7s rep%d wall %.3fs  decode %.2f ms (%.2f us/shot, %.0f shots/s) count %.3f ms h2d %.2f ms events/shot %.1f rounds/shot %.2f retried %d groups %d' % (
+            gspec, rep, dt, st.ms_decode, st.ms_decode * 1e3 / shots, shots / (st.ms_decode * 1e-3), st.ms_count, st.ms_h2d,
             st.num_detection_events / shots, st.matcher_rounds / shots, st.num_retried_shots, st.num_groups), flush=True)
     if ref is None:
         ref = (pred.copy(), wint.copy())
@@ -40,9 +44,9 @@ if check:
     oo, ow = oracle.OracleDecoder(text).decode_batch(dets[:n])
     print('  oracle check on %d shots: weight diffs %d obs diffs %d' % (n, (ow != ref[1][:n]).sum(), (oo != m[:n]).sum()))
 # phase profile of the first group width
-dec.set_tuning(group_threads=groups[0])
+tune(groups[0])
 dec.profile_phases(True)
 dec.decode_with_integer_weights(dets)
 ph = dec.profile_phases(False)
 tot = sum(v for k, v in ph.items() if k != 'shots')
-print('  phases (cycles/shot of thread 0, group=%d): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k != 'shots'))
+print('  phases (cycles/shot of thread 0, group=%s): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k != 'shots'))
