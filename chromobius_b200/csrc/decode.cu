@@ -218,7 +218,7 @@ struct cb200_decoder {
     DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list;
     DeviceBuf<unsigned long long> d_phase;
     bool profile_phases = false;
-    unsigned long long phase_cycles[8] = {};
+    unsigned long long phase_cycles[16] = {};
     DeviceBuf<float> d_wfloat;
     // arena layout currently initialised on the device
     ScratchConfig arena_cfg{};
@@ -483,8 +483,8 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     p.rounds_out = d->d_rounds.ptr;
     p.work_counter = d->d_scalars.ptr + 4;
     if (d->profile_phases) {
-        d->d_phase.ensure(8);
-        CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 64, s));
+        d->d_phase.ensure(16);
+        CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 128, s));
         p.phase_cycles = d->d_phase.ptr;
     }
     if (edges_out || num_edge_ints) {
@@ -574,7 +574,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         CUDA_CHECK(cudaStreamSynchronize(s));
         for (uint32_t r : rounds) st.matcher_rounds += r;
     }
-    if (d->profile_phases) CUDA_CHECK(cudaMemcpyAsync(d->phase_cycles, d->d_phase.ptr, 64, cudaMemcpyDeviceToHost, s));
+    if (d->profile_phases) CUDA_CHECK(cudaMemcpyAsync(d->phase_cycles, d->d_phase.ptr, 128, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaEventRecord(d->ev[5], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     st.kernel_launches = launches;
@@ -698,9 +698,9 @@ int cb200_set_groups_per_sm(cb200_decoder *d, uint32_t groups_per_sm) {
     return CB200_OK;
 }
 
-int cb200_profile_phases(cb200_decoder *d, int enable, unsigned long long *cycles_out8) {
+int cb200_profile_phases(cb200_decoder *d, int enable, unsigned long long *cycles_out16) {
     if (!d) return CB200_ERR_INVALID_ARGUMENT;
-    if (cycles_out8) memcpy(cycles_out8, d->phase_cycles, sizeof(d->phase_cycles));
+    if (cycles_out16) memcpy(cycles_out16, d->phase_cycles, sizeof(d->phase_cycles));
     d->profile_phases = enable != 0;
     return CB200_OK;
 }

@@ -35,8 +35,12 @@
 
 #ifdef __CUDACC__
 #define CB_HD __host__ __device__ __forceinline__
+// Large routines are kept out of line: the decode kernel is latency bound with many warps at different points of the
+// code, and a fully inlined body (several hundred KB of SASS) thrashes the instruction cache.
+#define CB_HDN __host__ __device__ __noinline__
 #else
 #define CB_HD inline
+#define CB_HDN inline
 #endif
 
 namespace cb200 {
@@ -99,6 +103,7 @@ struct DecodeParams {
     // optional profiling: cycles spent by thread 0 of every group in
     // [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
     // [5] path extraction [6] Euler tours + discharge [7] shots
+    // [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events; [12..15] their counts
     unsigned long long *phase_cycles;
 };
 
@@ -275,6 +280,7 @@ struct Shot {
     // dynamic region
     uint8_t *dyn;
     uint64_t dyn_cap;
+    unsigned long long *prof;  // DecodeParams::phase_cycles (nullable)
 
     CB_HD uint32_t event_node(uint32_t i) const { return 2 * evdet[i >> 1] + (i & 1); }
     CB_HD bool node_is_event(uint32_t node) const {
@@ -328,6 +334,7 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.used_flag = q; q += align16(m);
     s.dyn = q;
     s.dyn_cap = align16(p.cfg.dyn_bytes);
+    s.prof = p.phase_cycles;
     s.M = 0;
     // shared memory
     s.nwords = (p.T.num_dets + 31) / 32;
@@ -354,7 +361,7 @@ CB_HD void init_group_arena(Shot &s, const G &g) {
 
 // Exclusive prefix sum of arr[0..n) in place, cooperatively; returns the total. Needs g.n <= SCAN_TMP.
 template <class G>
-CB_HD uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t n) {
+CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t n) {
     uint32_t chunk = (n + g.n - 1) / g.n;
     uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
     if (lo > n) lo = n;
@@ -389,7 +396,7 @@ CB_HD uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t
 // Pad bits and ignored detectors are cleared by the ingest mask.
 // ---------------------------------------------------------------------------------------------------------------
 template <class G>
-CB_HD void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
+CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
     const uint32_t nb = s.T.num_det_bytes;
     for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
         uint32_t v = 0;
@@ -446,7 +453,10 @@ CB_HD int64_t ball_lookup(const BallTables &t, uint32_t node) {
 template <class G>
 CB_HD void ball_clear(BallTables &t, const G &g) {
     g.wsync();
-    for (uint32_t k = g.lane; k < t.nused; k += g.lanes) t.key[t.used[k]] = HT_EMPTY;
+    uint32_t *const key = t.key;
+    const uint32_t *const used = t.used;
+    const uint32_t n = t.nused;
+    for (uint32_t k = g.lane; k < n; k += g.lanes) key[used[k]] = HT_EMPTY;
     t.nused = t.nfront = 0;
     g.wsync();
 }
@@ -479,80 +489,104 @@ CB_HD const AdjEntry *adj_of(const TablesView &T) { return T.ell_shift ? T.ell_a
 // Other events settled inside the ball are appended to t.found when collect_events is set.
 // The tables are left populated (the caller clears them).
 template <class G>
-CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int64_t radius, uint32_t need_more_than,
-                    uint32_t stop_node, bool collect_events, bool inclusive, int64_t *limit_out, uint32_t *nfound_out) {
-    const uint32_t hmask = t.H - 1;
-    const AdjEntry *adj = adj_of(s.T);
-    if (g.lane == 0) {
-        uint32_t k = ht_hash(src, t.H);
-        t.key[k] = src;
-        t.dist[k] = 0;
-        t.fpos[k] = 0;
-        t.used[0] = k;
-        t.front[0] = k;
+CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int64_t radius, uint32_t need_more_than,
+                     uint32_t stop_node, bool collect_events, bool inclusive, int64_t *limit_out, uint32_t *nfound_out) {
+    // Everything the loop touches is copied into locals first: this routine is kept out of line, and fields reached
+    // through the references would otherwise be re-read from local memory on every use.
+    uint32_t *const key = t.key;
+    int64_t *const dist = t.dist;
+    uint32_t *const fpos = t.fpos;
+    uint32_t *const used = t.used;
+    uint64_t *const front = t.front;
+    NbEntry *const found = t.found;
+    const uint32_t H = t.H, hmask = t.H - 1, cap = t.cap, fcap = t.fcap;
+    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane_lt = (1u << lane) - 1;
+    const uint32_t ell_shift = s.T.ell_shift;
+    const AdjEntry *const adj = ell_shift ? s.T.ell_adj : s.T.adj;
+    const uint32_t *const row_ptr = s.T.row_ptr;
+    const uint32_t *const words = s.words;
+    const uint32_t *const word_rank = s.word_rank;
+    uint32_t nused = 1, nfront = 1;
+    if (lane == 0) {
+        uint32_t k = ht_hash(src, H);
+        key[k] = src;
+        dist[k] = 0;
+        fpos[k] = 0;
+        used[0] = k;
+        front[0] = k;
     }
-    t.nused = 1;
-    t.nfront = 1;
     g.wsync();
     uint32_t nfound = 0;
     int64_t limit = radius;
     int result = BALL_OK;
-    while (t.nfront) {
+    while (nfront) {
         // pop the closest open node
         uint64_t best = ~uint64_t{0};
-        for (uint32_t q = g.lane; q < t.nfront; q += g.lanes) {
-            uint64_t cand = t.front[q];
+        for (uint32_t q = lane; q < nfront; q += lanes) {
+            uint64_t cand = front[q];
             best = cand < best ? cand : best;
         }
         best = g.min64(best);
         const int64_t d = (int64_t)(best >> 20);
         const uint32_t slot = (uint32_t)(best & 0xFFFFF);
         if (limit >= 0 && (inclusive ? d > limit : d >= limit)) break;
-        const uint32_t u = t.key[slot];
-        const uint32_t q = t.fpos[slot];
+        const uint32_t u = key[slot];
+        const uint32_t q = fpos[slot];
         g.wsync();
-        if (g.lane == 0) {
-            uint64_t last = t.front[t.nfront - 1];
-            t.front[q] = last;
-            t.fpos[(uint32_t)(last & 0xFFFFF)] = q;
-            t.fpos[slot] = FRONT_CLOSED;
+        if (lane == 0) {
+            uint64_t last = front[nfront - 1];
+            front[q] = last;
+            fpos[(uint32_t)(last & 0xFFFFF)] = q;
+            fpos[slot] = FRONT_CLOSED;
         }
-        t.nfront--;
+        nfront--;
         g.wsync();
         if (u == stop_node) break;
-        if (collect_events && u != src && s.node_is_event(u)) {
-            if (nfound >= t.fcap) {
-                result = BALL_OVERFLOW;
-                break;
-            }
-            if (g.lane == 0) {
-                t.found[nfound].ev = s.node_event_index(u);
-                t.found[nfound].pad = 0;
-                t.found[nfound].d = d;
-            }
-            nfound++;
-            if (limit < 0 && nfound > need_more_than) {
-                limit = d;
-                break;
+        if (collect_events && u != src) {
+            const uint32_t det = u >> 1;
+            const uint32_t w = words[det >> 5];
+            if ((w >> (det & 31)) & 1) {
+                if (nfound >= fcap) {
+                    result = BALL_OVERFLOW;
+                    break;
+                }
+                if (lane == 0) {
+                    found[nfound].ev = 2 * (word_rank[det >> 5] + popc32(w & ((1u << (det & 31)) - 1))) + (u & 1);
+                    found[nfound].pad = 0;
+                    found[nfound].d = d;
+                }
+                nfound++;
+                if (limit < 0 && nfound > need_more_than) {
+                    limit = d;
+                    break;
+                }
             }
         }
-        const RowRange row = row_of(s.T, u);
-        if (t.nused + (row.e1 - row.e0) > t.cap) {
+        uint32_t e0, e1;
+        if (ell_shift) {
+            e0 = u << ell_shift;
+            e1 = e0 + (1u << ell_shift);
+        } else {
+            e0 = row_ptr[u];
+            e1 = row_ptr[u + 1];
+        }
+        if (nused + (e1 - e0) > cap) {
             result = BALL_OVERFLOW;
             break;
         }
-        for (uint32_t base = row.e0; base < row.e1; base += g.lanes) {
-            const uint32_t e = base + g.lane;
+        for (uint32_t base = e0; base < e1; base += lanes) {
+            const uint32_t e = base + lane;
             bool is_new = false;
             uint32_t my_slot = 0;
             int64_t nd = 0;
-            if (e < row.e1) {
+            if (e < e1) {
                 AdjEntry a = adj[e];
                 nd = d + a.wt;
                 if (a.nbr != NO_INDEX && !(limit >= 0 && (inclusive ? nd > limit : nd >= limit))) {
-                    uint32_t k = ht_hash(a.nbr, t.H);
+                    uint32_t k = ht_hash(a.nbr, H);
                     while (true) {
-                        uint32_t old = cb_atomic_cas(&t.key[k], HT_EMPTY, a.nbr);
+                        uint32_t old = cb_atomic_cas(&key[k], HT_EMPTY, a.nbr);
                         if (old == HT_EMPTY) {
                             is_new = true;
                             break;
@@ -562,29 +596,31 @@ CB_HD int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int6
                     }
                     my_slot = k;
                     if (is_new) {
-                        t.dist[k] = nd;
+                        dist[k] = nd;
                     } else {
-                        uint32_t fp = t.fpos[k];
-                        if (fp != FRONT_CLOSED && nd < t.dist[k]) {
-                            t.dist[k] = nd;
-                            t.front[fp] = ((uint64_t)nd << 20) | k;
+                        uint32_t fp = fpos[k];
+                        if (fp != FRONT_CLOSED && nd < dist[k]) {
+                            dist[k] = nd;
+                            front[fp] = ((uint64_t)nd << 20) | k;
                         }
                     }
                 }
             }
             const uint32_t fresh = g.ballot(is_new);
             if (is_new) {
-                uint32_t idx = popc32(fresh & ((1u << g.lane) - 1));
-                t.used[t.nused + idx] = my_slot;
-                t.front[t.nfront + idx] = ((uint64_t)nd << 20) | my_slot;
-                t.fpos[my_slot] = t.nfront + idx;
+                uint32_t idx = popc32(fresh & lane_lt);
+                used[nused + idx] = my_slot;
+                front[nfront + idx] = ((uint64_t)nd << 20) | my_slot;
+                fpos[my_slot] = nfront + idx;
             }
             const uint32_t c = popc32(fresh);
-            t.nused += c;
-            t.nfront += c;
+            nused += c;
+            nfront += c;
             g.wsync();
         }
     }
+    t.nused = nused;
+    t.nfront = nfront;
     if (result == BALL_OK && limit < 0) result = BALL_EXHAUSTED;
     *limit_out = limit;
     *nfound_out = nfound;
@@ -595,15 +631,15 @@ CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry 
 
 // Grows the ball of event i (one warp). Writes nb_off/nb_cnt/R of event i and marks i and every reported event dirty.
 template <class G>
-CB_HD void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
+CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
     const uint32_t src = s.event_node(i);
     int64_t limit = 0;
     uint32_t nfound = 0;
-    BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
-    int r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, false, &limit, &nfound);
-    if (r == BALL_OVERFLOW && t == &s.sh_ball) {
-        ball_clear(*t, g);
-        t = &s.gl_ball;
+    BallTables *t = nullptr;
+    int r = BALL_OVERFLOW;
+    for (int attempt = s.sh_ball.H ? 0 : 1; attempt < 2 && r == BALL_OVERFLOW; attempt++) {
+        if (t) ball_clear(*t, g);
+        t = attempt ? &s.gl_ball : &s.sh_ball;
         r = ball_grow(s, g, *t, src, radius, need_more_than, NO_INDEX, true, false, &limit, &nfound);
     }
     ball_clear(*t, g);
@@ -715,7 +751,7 @@ struct Blossom {
     CB_HD void update_slack(int u, int x) {
         if (!slack[x] || edist(u, x) < edist(slack[x], x)) slack[x] = (uint16_t)u;
     }
-    CB_HD void set_slack(int x) {
+    CB_HDN void set_slack(int x) {
         slack[x] = 0;
         for (int u = 1; u <= n; ++u)
             if (has(u, x) && st[u] != x && S[st[u]] == 0) update_slack(u, x);
@@ -726,7 +762,7 @@ struct Blossom {
         if (qt == qh) broken = true;
     }
     // depth-first, children in order
-    CB_HD void q_push(int x) {
+    CB_HDN void q_push(int x) {
         int sp = 0;
         stk[sp++] = (uint16_t)x;
         while (sp) {
@@ -739,7 +775,7 @@ struct Blossom {
             for (int i = fl_len[y] - 1; i >= 0; --i) stk[sp++] = f[i];
         }
     }
-    CB_HD void set_st(int x, int b) {
+    CB_HDN void set_st(int x, int b) {
         int sp = 0;
         stk[sp++] = (uint16_t)x;
         while (sp) {
@@ -757,7 +793,7 @@ struct Blossom {
             f[b] = t;
         }
     }
-    CB_HD int get_pr(int b, int xr) {
+    CB_HDN int get_pr(int b, int xr) {
         uint16_t *f = flower(b);
         int len = fl_len[b];
         int pr = 0;
@@ -775,7 +811,7 @@ struct Blossom {
         for (int a = 0, b = len - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
     }
     // set_match(u, v) with an explicit stack of (u, v) pairs.
-    CB_HD void set_match(int u0, int v0) {
+    CB_HDN void set_match(int u0, int v0) {
         int sp = 0;
         stk[sp++] = (uint16_t)u0;
         stk[sp++] = (uint16_t)v0;
@@ -797,7 +833,7 @@ struct Blossom {
             rotate_left(f, fl_len[u], pr);
         }
     }
-    CB_HD void augment(int u, int v) {
+    CB_HDN void augment(int u, int v) {
         for (;;) {
             int xnv = st[match[u]];
             set_match(u, v);
@@ -807,7 +843,7 @@ struct Blossom {
             v = xnv;
         }
     }
-    CB_HD int get_lca(int u, int v) {
+    CB_HDN int get_lca(int u, int v) {
         for (++vis_t; u || v;) {
             if (u != 0) {
                 if (vis[u] == vis_t) return u;
@@ -819,7 +855,7 @@ struct Blossom {
         }
         return 0;
     }
-    CB_HD void add_blossom(int u, int lca, int v) {
+    CB_HDN void add_blossom(int u, int lca, int v) {
         int b = n + 1;
         while (b <= n_x && st[b]) ++b;
         if (b > n_x) ++n_x;
@@ -861,7 +897,7 @@ struct Blossom {
         }
         set_slack(b);
     }
-    CB_HD void expand_blossom(int b) {
+    CB_HDN void expand_blossom(int b) {
         uint16_t *f = flower(b);
         int len = fl_len[b];
         for (int i = 0; i < len; ++i) set_st(f[i], f[i]);
@@ -886,7 +922,7 @@ struct Blossom {
         st[b] = 0;
     }
     // e = best edge between nodes a (row) and b: endpoints (eu in a, ev in b)
-    CB_HD bool on_found_edge(int eu, int ev) {
+    CB_HDN bool on_found_edge(int eu, int ev) {
         int u = st[eu], v = st[ev];
         if (S[v] == -1) {
             pa[v] = (uint16_t)eu;
@@ -906,7 +942,7 @@ struct Blossom {
         }
         return false;
     }
-    CB_HD bool matching() {
+    CB_HDN bool matching() {
         const int64_t INF = INT64_MAX / 4;
         for (int x = 1; x <= n_x; ++x) {
             S[x] = -1;
@@ -964,7 +1000,7 @@ struct Blossom {
         }
     }
     // W must be filled (symmetric, 0 = absent). Returns the number of matched pairs; match[1..n] holds partners.
-    CB_HD int solve() {
+    CB_HDN int solve() {
         n_x = n;
         vis_t = 0;
         for (int u = 0; u < NX; ++u) {
@@ -1037,7 +1073,7 @@ CB_HD void request_growth(Shot &s, uint32_t ev, int64_t to) {
 
 // First pass over component c, one thread per component: sorts the members, handles odd components (everyone grows)
 // and single-edge components (closed form). Returns false when the component needs the blossom solver.
-CB_HD bool solve_component_small(Shot &s, uint32_t c) {
+CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     uint32_t r = s.comp_root[c];
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
@@ -1073,7 +1109,7 @@ CB_HD bool solve_component_small(Shot &s, uint32_t c) {
 
 // Exact solve of component c by the dense blossom, on one thread. `scratch` (nullable) is fast memory the solver may
 // use when the component fits; otherwise the scratch comes from the dynamic region.
-CB_HD void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
+CB_HDN void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
     uint32_t r = s.comp_root[c];
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
@@ -1084,6 +1120,7 @@ CB_HD void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64
     uint64_t need_bytes = Blossom::bytes_needed((int)n);
     uint8_t *memory = (scratch && need_bytes <= scratch_bytes) ? scratch : s.alloc(need_bytes);
     if (!memory) return;
+    const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     Blossom bl;
     bl.bind(memory, (int)n);
     for (uint32_t a = 0; a < n; a++) s.lidx[mem[a]] = a + 1;
@@ -1103,6 +1140,11 @@ CB_HD void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64
         }
     }
     int pairs = bl.solve();
+    if (s.prof) {
+        int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
+        cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
+        cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
+    }
     if (bl.broken) {
         s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
@@ -1125,7 +1167,7 @@ CB_HD void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64
 }
 
 template <class G>
-CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
+CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     const uint32_t M = s.M;
     for (uint32_t i = g.tid; i < M; i += g.n) {
         s.partner[i] = -1;
@@ -1225,15 +1267,15 @@ CB_HD uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 // sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
 template <class G>
-CB_HD void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_total) {
+CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_total) {
     const uint32_t src = s.event_node(i), dst = s.event_node(j);
     int64_t limit = 0;
     uint32_t nfound = 0;
-    BallTables *t = s.sh_ball.H ? &s.sh_ball : &s.gl_ball;
-    int r = ball_grow(s, g, *t, src, d_total, 0, dst, false, true, &limit, &nfound);
-    if (r == BALL_OVERFLOW && t == &s.sh_ball) {
-        ball_clear(*t, g);
-        t = &s.gl_ball;
+    BallTables *t = nullptr;
+    int r = BALL_OVERFLOW;
+    for (int attempt = s.sh_ball.H ? 0 : 1; attempt < 2 && r == BALL_OVERFLOW; attempt++) {
+        if (t) ball_clear(*t, g);
+        t = attempt ? &s.gl_ball : &s.sh_ball;
         r = ball_grow(s, g, *t, src, d_total, 0, dst, false, true, &limit, &nfound);
     }
     bool ok = r == BALL_OK;
@@ -1309,7 +1351,7 @@ CB_HD void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_t
 }
 
 template <class G>
-CB_HD void paths_shot(Shot &s, const G &g) {
+CB_HDN void paths_shot(Shot &s, const G &g) {
     for (uint32_t i = g.tid; i < s.M; i += g.n) s.path_len[i] = 0;
     g.sync();
     uint64_t wsum = 0;
@@ -1348,7 +1390,7 @@ CB_HD uint32_t find_half_edge(const TablesView &T, uint32_t from, uint32_t to) {
 }
 
 // decoder.cc:80-138. `used` bookkeeping is a per-detection-event flag instead of a linear search.
-CB_HD bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len, uint32_t start, uint64_t *out) {
+CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len, uint32_t start, uint64_t *out) {
     OptMask cur;
     cur.has = 1u << start;
     cur.v[0] = cur.v[1] = cur.v[2] = cur.v[3] = 0;
@@ -1435,7 +1477,7 @@ struct LiftArrays {
 };
 
 // Tours and discharges one component. Runs on one thread.
-CB_HD void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc) {
+CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc) {
     auto look_next = [&](uint32_t sl) -> uint32_t {  // euler_tours.cc:34-45
         while (true) {
             uint32_t p = L.lstart[sl] + L.fillc[sl];
@@ -1489,7 +1531,7 @@ CB_HD void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t 
 }
 
 template <class G>
-CB_HD void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
+CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
     const uint32_t M = s.M;
     // edge numbering: exclusive scan of (path_len - 1) over events -> s.start
     for (uint32_t i = g.tid; i < M; i += g.n) s.start[i] = s.path_len[i] ? s.path_len[i] - 1 : 0;

@@ -105,8 +105,9 @@ int cb200_set_groups_per_sm(cb200_decoder *dec, uint32_t groups_per_sm);
 /* Phase profiling of the decode kernel (clock64 of thread 0 of every group, summed over shots). Enables/disables it
  * for later calls and copies out the counters of the most recent profiled call:
  * [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
- * [5] path extraction [6] Euler tours + discharge [7] number of shots. */
-int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cycles_out8);
+ * [5] path extraction [6] Euler tours + discharge [7] number of shots
+ * [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events, [12..15] how many of each. */
+int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cycles_out16);
 
 /* Sizes of the device-resident tables, for DESIGN.md / bench reporting. */
 uint64_t cb200_table_bytes(const cb200_decoder *dec);

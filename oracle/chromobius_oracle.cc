@@ -1202,10 +1202,11 @@ struct Decoder {
         out->weight = 0;
         int m = (int)events.size();
         if (m == 0) return true;
-        if (matcher_mode == 1 || (matcher_mode == 0 && m > 160)) {
+        if (matcher_mode == 1 || matcher_mode == 3 || (matcher_mode == 0 && m > 160)) {
             std::vector<int> partner;
             std::vector<int64_t> pdist;
-            if (!match_events_local(events, &partner, &pdist)) return false;
+            if (matcher_mode == 3 ? !match_events_lazy(events, &partner, &pdist) : !match_events_local(events, &partner, &pdist))
+                return false;
             for (int i = 0; i < m; i++) {
                 int j = partner[i];
                 if (j > i) {
@@ -1392,6 +1393,7 @@ struct Decoder {
                     }
                     continue;
                 }
+                stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
                 std::vector<int> &loc = loc_buf;
                 loc.resize(m);
                 for (int k = 0; k < n; k++) loc[mem[k]] = k + 1;
@@ -1437,6 +1439,153 @@ struct Decoder {
             }
         }
         for (int i = 0; i < m; i++) event_index[events[i]] = -1;
+        if (!ok) last_error = "No perfect matching exists for the detection events.";
+        return ok;
+    }
+
+    // Certified local matching with lazy merging. Same certificate as match_events_local, but solved components keep
+    // their doubled duals h (= 2 y): balls that grow only force a re-solve when a newly seen pair violates
+    // h_a + h_b <= 2 d(a, b); otherwise the old component solutions stay optimal together and nothing is re-solved.
+    // Final state: every event solved, h_a <= R_a for all a (covers unseen pairs) and h_a + h_b <= 2 d(a, b) for every
+    // seen pair in different components, so the union of the component matchings is a global optimum.
+    uint64_t stat_blossoms[4] = {0, 0, 0, 0};  // component sizes <= 8, <= 16, <= 32, > 32
+    uint64_t stat_rounds = 0, stat_pairs_closed_form = 0;
+    bool match_events_lazy(const std::vector<uint64_t> &events, std::vector<int> *partner_out, std::vector<int64_t> *pdist_out) {
+        int m = (int)events.size();
+        partner_out->assign(m, -1);
+        pdist_out->assign(m, 0);
+        if (m == 0) return true;
+        for (int i = 0; i < m; i++) event_index[events[i]] = i;
+        std::vector<int64_t> R(m), h(m, 0);
+        std::vector<std::vector<std::pair<int, int64_t>>> nb(m);
+        std::vector<char> solved(m, 0), regrown(m, 0), stale(m, 0);
+        std::vector<int> pc(m, -1);
+        bool ok = true;
+        for (int i = 0; i < m && ok; i++) {
+            R[i] = ball((node_t)events[i], -1, 0, &nb[i]);
+            if (R[i] < 0) ok = false;
+        }
+        std::vector<int> uf(m);
+        std::vector<std::pair<int, int64_t>> grow;
+        std::vector<std::pair<int, int>> by_root(m);
+        std::vector<int> mem;
+        for (int round = 0; ok; round++) {
+            if (round > 64) {
+                ok = false;
+                break;
+            }
+            stat_rounds++;
+            for (int i = 0; i < m; i++) uf[i] = i;
+            auto find = [&](int x) {
+                while (uf[x] != x) {
+                    uf[x] = uf[uf[x]];
+                    x = uf[x];
+                }
+                return x;
+            };
+            auto unite = [&](int a, int b) {
+                a = find(a);
+                b = find(b);
+                if (a != b) uf[std::max(a, b)] = std::min(a, b);
+            };
+            for (int i = 0; i < m; i++)
+                if (solved[i]) unite(i, pc[i]);
+            for (int i = 0; i < m; i++)
+                for (auto &p : nb[i]) {
+                    int j = p.first;
+                    if (!solved[i] || !solved[j] || h[i] + h[j] > 2 * p.second) {
+                        // a violated pair inside one solved component is either an old blossom-internal edge or a pair
+                        // first seen after the solve; only a ball that grew since then can have produced the latter
+                        if (solved[i] && solved[j] && pc[i] == pc[j] && regrown[i]) stale[pc[i]] = 1;
+                        unite(i, j);
+                    }
+                }
+            for (int i = 0; i < m; i++) by_root[i] = {find(i), i};
+            std::sort(by_root.begin(), by_root.end());
+            grow.clear();
+            for (int a = 0; a < m;) {
+                int b = a;
+                mem.clear();
+                while (b < m && by_root[b].first == by_root[a].first) mem.push_back(by_root[b++].second);
+                a = b;
+                bool needs_solve = false;
+                for (int i : mem) needs_solve |= !solved[i] || pc[i] != pc[mem[0]] || stale[pc[i]];
+                for (int i : mem) regrown[i] = 0;
+                if (!needs_solve) continue;
+                for (int i : mem)
+                    if (pc[i] >= 0) stale[pc[i]] = 0;
+                int n = (int)mem.size();
+                if (n % 2) {
+                    for (int i : mem) {
+                        grow.push_back({i, -1});
+                        solved[i] = 0;
+                    }
+                    continue;
+                }
+                if (n == 2) {
+                    int i = mem[0], j = mem[1];
+                    int64_t d = -1;
+                    for (auto &p : nb[i])
+                        if (p.first == j) d = p.second;
+                    for (auto &p : nb[j])
+                        if (p.first == i) d = p.second;
+                    stat_pairs_closed_form++;
+                    for (int e : mem) {
+                        h[e] = d;
+                        solved[e] = 1;
+                        pc[e] = mem[0];
+                        if (d > R[e]) grow.push_back({e, d});
+                    }
+                    (*partner_out)[i] = j;
+                    (*partner_out)[j] = i;
+                    (*pdist_out)[i] = (*pdist_out)[j] = d;
+                    continue;
+                }
+                stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
+                std::vector<int> &loc = loc_buf;
+                loc.resize(m);
+                for (int k = 0; k < n; k++) loc[mem[k]] = k + 1;
+                int64_t big = 2;
+                for (int i : mem)
+                    for (auto &p : nb[i])
+                        if (find(p.first) == by_root[a - 1].first) big = std::max(big, p.second + 2);
+                DenseBlossom &bl = local_blossom;
+                bl.init(n);
+                for (int i : mem)
+                    for (auto &p : nb[i])
+                        if (find(p.first) == by_root[a - 1].first) bl.add_edge(loc[i], loc[p.first], big - p.second);
+                int cnt = bl.solve();
+                if (cnt * 2 != n) {
+                    for (int i : mem) {
+                        solved[i] = 0;
+                        if (!bl.match[loc[i]]) grow.push_back({i, -1});
+                    }
+                    continue;
+                }
+                for (int i : mem) {
+                    int j = mem[bl.match[loc[i]] - 1];
+                    (*partner_out)[i] = j;
+                    for (auto &p : nb[i])
+                        if (p.first == j) (*pdist_out)[i] = (*pdist_out)[j] = p.second;
+                    h[i] = big - bl.lab[loc[i]];
+                    solved[i] = 1;
+                    pc[i] = mem[0];
+                    if (h[i] > R[i]) grow.push_back({i, h[i]});
+                }
+            }
+            if (grow.empty()) break;
+            for (auto &[i, to] : grow) {
+                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i]);
+                if (R[i] < 0) {
+                    ok = false;
+                    break;
+                }
+                regrown[i] = 1;
+            }
+        }
+        for (int i = 0; i < m; i++) event_index[events[i]] = -1;
+        if (ok)
+            for (int i = 0; i < m; i++) ok &= solved[i] != 0;
         if (!ok) last_error = "No perfect matching exists for the detection events.";
         return ok;
     }
@@ -1691,6 +1840,16 @@ double orc_normalising_constant(void *h) { return ((Decoder *)h)->t->normalising
 uint64_t orc_drag_ambiguities(void *h) { return ((Decoder *)h)->t->drag_ambiguities; }
 uint64_t orc_radius_retries(void *h) { return ((Decoder *)h)->stat_radius_retries; }
 void orc_set_matcher_mode(void *h, int mode) { ((Decoder *)h)->matcher_mode = mode; }
+void orc_matcher_stats(void *h, uint64_t *out6, int reset) {
+    auto *d = (Decoder *)h;
+    for (int k = 0; k < 4; k++) out6[k] = d->stat_blossoms[k];
+    out6[4] = d->stat_rounds;
+    out6[5] = d->stat_pairs_closed_form;
+    if (reset) {
+        for (int k = 0; k < 4; k++) d->stat_blossoms[k] = 0;
+        d->stat_rounds = d->stat_pairs_closed_form = 0;
+    }
+}
 
 // Caller frees with orc_free_str.
 char *orc_describe(void *h) {

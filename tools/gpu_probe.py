@@ -48,5 +48,7 @@ tune(groups[0])
 dec.profile_phases(True)
 dec.decode_with_integer_weights(dets)
 ph = dec.profile_phases(False)
-tot = sum(v for k, v in ph.items() if k != 'shots')
-print('  phases (cycles/shot of thread 0, group=%s): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k != 'shots'))
+main = ['ingest', 'explore_first', 'components', 'solve', 'explore_regrow', 'paths', 'lift']
+tot = sum(ph[k] for k in main)
+print('  phases (cycles/shot of thread 0, group=%s): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k in main))
+print('  blossoms per shot / cycles each: ' + ', '.join('%s: %.1f x %.0f' % (b, ph['n_' + b] / max(ph['shots'], 1), ph['blossom_' + b] / max(ph['n_' + b], 1)) for b in ['le8', 'le16', 'le32', 'gt32']))
