@@ -355,7 +355,7 @@ struct Plan {
 Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, double mean_det_events, uint32_t escalation) {
     Plan pl{};
     uint32_t group = d->tune_group;
-    if (group == 0) group = mean_det_events >= 24 ? 128 : 32;
+    if (group == 0) group = mean_det_events >= 200 ? 256 : (mean_det_events >= 8 ? 128 : 32);
     if (group != 32 && group != 128 && group != 256 && group != 512) group = 32;
     pl.group = group;
     uint32_t full = 4;
