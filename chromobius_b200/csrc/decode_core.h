@@ -197,7 +197,7 @@ struct GroupHeader {
     uint32_t lift_ncomp;
     uint32_t lift_cyc_top;
     uint32_t nbig;
-    uint32_t pad[1];
+    uint32_t nhuge;
 };
 
 // Ball tables of one warp: open-addressing hash (node -> distance, frontier position) plus the frontier itself.
@@ -262,6 +262,8 @@ struct Shot {
     GroupHeader *hdr;
     uint32_t *scan_tmp;    // [SCAN_TMP]
     BallTables sh_ball;    // this warp's shared-memory tables (H == 0: none)
+    uint8_t *sh_tables;    // all warps' shared-memory tables, contiguous (scratch for large blossoms)
+    uint64_t sh_tables_bytes;
     BallTables gl_ball;    // this warp's global-memory fallback tables
     uint32_t *node_slot;   // [num_nodes] persistent-clean
     uint32_t *words;       // masked detection-event bits as little-endian u32 words (shared memory)
@@ -282,6 +284,7 @@ struct Shot {
     uint64_t dyn_cap;
     unsigned long long *prof;  // DecodeParams::phase_cycles (nullable)
 
+    CB_HD uint32_t *lidx_huge() const { return fillp; }  // free between the member fill and the path phase
     CB_HD uint32_t event_node(uint32_t i) const { return 2 * evdet[i >> 1] + (i & 1); }
     CB_HD bool node_is_event(uint32_t node) const {
         uint32_t d = node >> 1;
@@ -343,6 +346,8 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.word_rank = (uint32_t *)sh; sh += align16((uint64_t{s.nwords} + 1) * 4);
     uint64_t sb = ball_table_bytes(p.cfg.sh_ht_log2, p.cfg.sh_found);
     bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, p.cfg.sh_ht_log2, p.cfg.sh_found);
+    s.sh_tables = sh;
+    s.sh_tables_bytes = (uint64_t)g.nwarps * sb;
 }
 
 // Called once per group before the first shot of a launch (shared memory does not survive launches).
@@ -678,10 +683,22 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
 // Dense primal-dual blossom (maximum weight among maximum-cardinality matchings) over one component.
 // Vertices 1..n, blossoms n+1..NX-1. Edge (u, v) exists iff W[u][v] > 0. Doubled duals `lab` as in the classic
 // O(n^3) formulation: lab[u] + lab[v] >= 2 W(u, v), tight on matched edges.
-// All storage is caller provided (Shot::alloc); recursion is replaced by explicit stacks.
+// All storage is caller provided; recursion is replaced by explicit stacks.
+//
+// Execution: the primal-dual bookkeeping (trees, blossoms, augmentations) is sequential and runs on lane 0 of the warp
+// ("master"). Its O(n) / O(n^2) inner loops -- slack recomputation, the dual step, blossom row merges, initialisation --
+// are data parallel and are executed by all 32 lanes: lanes 1..31 sit in worker_loop() and execute the helper the
+// master announces through a small command block, synchronising with __syncwarp (which does not require the lanes to
+// be at the same program counter). Every helper reproduces the sequential loop's result exactly (ties go to the
+// lowest index), so the matching and the duals do not depend on the number of lanes. Small components run on the
+// master alone (`par == false`), and so does the host build (one lane).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int BLOSSOM_PAR_MIN = 12;  // components with at least this many events use the warp helpers
+
+template <class G>
 struct Blossom {
-    int n, n_x, NX, FL;
+    enum Op : uint32_t { OP_EXIT = 0, OP_INIT, OP_SET_SLACK, OP_DUAL_MIN, OP_LAB_UPDATE, OP_NEXT_TIGHT, OP_BLOSSOM_CLEAR, OP_MERGE_ROW, OP_PHASE_INIT };
+    int n, n_x, NX, FL, AW;
     int64_t *W;        // (n+1) x (n+1)
     uint8_t *ge;       // NX x NX x 2 : original endpoints (eu, ev) of the best edge between two nodes; eu == 0: none
     int64_t *lab;      // NX
@@ -693,13 +710,18 @@ struct Blossom {
     uint16_t *fl_len;  // NX
     uint16_t *q;       // circular queue, capacity QC
     uint16_t *stk;     // explicit stack, capacity 2*NX
+    uint32_t *adjm;    // (n+1) x AW adjacency bit rows: bit v of row u <=> W[u][v] > 0
+    uint32_t *cmd;     // [8] command block (master -> workers)
     int qh, qt, QC;
     uint32_t vis_t;
     bool broken;
+    bool par;
+    G g;
 
     static CB_HD uint64_t bytes_needed(int n) {
         int NX = n + n / 2 + 2;
         int FL = n + 2;
+        int AW = (n + 32) / 32;
         uint64_t b = 0;
         b += align16(uint64_t(n + 1) * (n + 1) * 8);
         b += align16(uint64_t(NX) * NX * 2);
@@ -712,13 +734,17 @@ struct Blossom {
         b += align16(uint64_t(NX) * 2);
         b += align16(uint64_t(2 * n + 4) * 2);
         b += align16(uint64_t(2 * NX + 4) * 2);
+        b += align16(uint64_t(n + 1) * AW * 4);
+        b += 32;
         return b;
     }
-    CB_HD void bind(uint8_t *mem, int n_) {
+    CB_HD void bind(uint8_t *mem, int n_, const G &g_) {
+        g = g_;
         n = n_;
         NX = n + n / 2 + 2;
         FL = n + 2;
         QC = 2 * n + 4;
+        AW = (n + 32) / 32;
         uint8_t *p = mem;
         W = (int64_t *)p; p += align16(uint64_t(n + 1) * (n + 1) * 8);
         ge = p; p += align16(uint64_t(NX) * NX * 2);
@@ -733,8 +759,12 @@ struct Blossom {
         fl = (uint16_t *)p; p += align16(uint64_t(NX - n) * FL * 2);
         fl_len = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
         q = (uint16_t *)p; p += align16(uint64_t(QC) * 2);
-        stk = (uint16_t *)p;
+        stk = (uint16_t *)p; p += align16(uint64_t(2 * NX + 4) * 2);
+        adjm = (uint32_t *)p; p += align16(uint64_t(n + 1) * AW * 4);
+        cmd = (uint32_t *)p;
         broken = false;
+        par = g.lanes > 1 && n >= BLOSSOM_PAR_MIN;
+        n_x = n;
     }
     CB_HD int64_t &w(int u, int v) { return W[u * (n + 1) + v]; }
     CB_HD uint8_t &geu(int a, int b) { return ge[(a * NX + b) * 2]; }
@@ -745,16 +775,197 @@ struct Blossom {
         return lab[eu] + lab[ev] - 2 * W[eu * (n + 1) + ev];
     }
     CB_HD uint16_t *flower(int b) { return fl + (b - n) * FL; }
-    CB_HD int flen(int b) { return b <= n ? 0 : fl_len[b]; }
     CB_HD uint16_t &ffrom(int b, int x) { return ff[b * (n + 1) + x]; }
 
+    // ---- data-parallel kernels: executed by every participating lane (`lane`, `lanes` = 0, 1 when running alone) ----
+    CB_HD void k_init(int lane, int lanes) {
+        for (int u = lane; u < NX; u += lanes) {
+            match[u] = 0;
+            st[u] = (uint16_t)(u <= n ? u : 0);
+            fl_len[u] = 0;
+            vis[u] = 0;
+            slack[u] = 0;
+            pa[u] = 0;
+            S[u] = -1;
+            lab[u] = 0;
+        }
+        for (int u = 1 + lane; u <= n; u += lanes) {
+            for (int k = 0; k < AW; k++) adjm[u * AW + k] = 0;
+            for (int v = 1; v <= n; ++v) {
+                ffrom(u, v) = (uint16_t)(u == v ? u : 0);
+                int64_t x = W[u * (n + 1) + v];
+                if (x > 0) {
+                    geu(u, v) = (uint8_t)u;
+                    gev(u, v) = (uint8_t)v;
+                    adjm[u * AW + (v >> 5)] |= 1u << (v & 31);
+                } else {
+                    geu(u, v) = 0;
+                    gev(u, v) = 0;
+                }
+            }
+        }
+    }
+    // max W, reduced across lanes by the caller
+    CB_HD int64_t k_wmax(int lane, int lanes) {
+        int64_t w_max = 0;
+        for (int u = 1 + lane; u <= n; u += lanes)
+            for (int v = 1; v <= n; ++v) {
+                int64_t x = W[u * (n + 1) + v];
+                if (x > w_max) w_max = x;
+            }
+        return w_max;
+    }
+    CB_HD void k_set_lab(int lane, int lanes, int64_t v) {
+        for (int u = 1 + lane; u <= n; u += lanes) lab[u] = v;
+    }
+    // (distance << 16 | u) of the best eligible vertex for slack[x]; ~0 when none. Lowest u wins ties.
+    CB_HD uint64_t k_set_slack(int lane, int lanes, int x) {
+        uint64_t best = ~uint64_t{0};
+        for (int u = 1 + lane; u <= n; u += lanes)
+            if (has(u, x) && st[u] != x && S[st[u]] == 0) {
+                uint64_t key = ((uint64_t)edist(u, x) << 16) | (uint64_t)u;
+                if (key < best) best = key;
+            }
+        return best;
+    }
+    CB_HD uint64_t k_dual_min(int lane, int lanes, int nx) {
+        uint64_t d = (uint64_t)(INT64_MAX / 4);
+        for (int b = n + 1 + lane; b <= nx; b += lanes)
+            if (st[b] == b && S[b] == 1) {
+                uint64_t v = (uint64_t)(lab[b] / 2);
+                if (v < d) d = v;
+            }
+        for (int x = 1 + lane; x <= nx; x += lanes)
+            if (st[x] == x && slack[x]) {
+                int64_t sd = edist(slack[x], x);
+                if (S[x] == -1) {
+                    if ((uint64_t)sd < d) d = (uint64_t)sd;
+                } else if (S[x] == 0) {
+                    if ((uint64_t)(sd / 2) < d) d = (uint64_t)(sd / 2);
+                }
+            }
+        return d;
+    }
+    CB_HD void k_lab_update(int lane, int lanes, int nx, int64_t d) {
+        for (int u = 1 + lane; u <= n; u += lanes) {
+            if (S[st[u]] == 0) lab[u] -= d;
+            else if (S[st[u]] == 1) lab[u] += d;
+        }
+        for (int b = n + 1 + lane; b <= nx; b += lanes)
+            if (st[b] == b) {
+                if (S[b] == 0) lab[b] += d * 2;
+                else if (S[b] == 1) lab[b] -= d * 2;
+            }
+    }
+    CB_HD bool tight_candidate(int x) {
+        return st[x] == x && slack[x] && st[slack[x]] != x && edist(slack[x], x) == 0;
+    }
+    CB_HD void k_blossom_clear(int lane, int lanes, int b, int nx) {
+        for (int x = 1 + lane; x <= nx; x += lanes) geu(b, x) = geu(x, b) = 0;
+        for (int x = 1 + lane; x <= n; x += lanes) ffrom(b, x) = 0;
+    }
+    CB_HD void k_merge_row(int lane, int lanes, int b, int xs, int nx) {
+        for (int x = 1 + lane; x <= nx; x += lanes)
+            if (has(xs, x) && (!has(b, x) || edist(xs, x) < edist(b, x))) {
+                geu(b, x) = geu(xs, x);
+                gev(b, x) = gev(xs, x);
+                geu(x, b) = geu(x, xs);
+                gev(x, b) = gev(x, xs);
+            }
+        for (int x = 1 + lane; x <= n; x += lanes)
+            if (ffrom(xs, x)) ffrom(b, x) = (uint16_t)xs;
+    }
+    CB_HD void k_phase_init(int lane, int lanes, int nx) {
+        for (int x = 1 + lane; x <= nx; x += lanes) {
+            S[x] = -1;
+            slack[x] = 0;
+        }
+    }
+
+    // ---- warp dispatch: every lane runs the same helper; results are reduced with warp primitives ----
+    CB_HDN uint64_t dispatch(uint32_t op, uint32_t a0, uint32_t a1, uint32_t a2) {
+        const int lane = g.lane, lanes = g.lanes;
+        uint64_t r = 0;
+        switch (op) {
+            case OP_INIT: {
+                k_init(lane, lanes);
+                int64_t wm = (int64_t)(~g.min64(~(uint64_t)k_wmax(lane, lanes)));  // max via min of complements
+                g.wsync();
+                k_set_lab(lane, lanes, wm);
+                break;
+            }
+            case OP_SET_SLACK:
+                r = g.min64(k_set_slack(lane, lanes, (int)a0));
+                break;
+            case OP_DUAL_MIN:
+                r = g.min64(k_dual_min(lane, lanes, (int)a0));
+                break;
+            case OP_LAB_UPDATE:
+                k_lab_update(lane, lanes, (int)a0, (int64_t)(((uint64_t)a2 << 32) | a1));
+                break;
+            case OP_NEXT_TIGHT: {
+                // smallest x >= a0 that is a tight candidate, or a1 + 1
+                int nx = (int)a1;
+                r = (uint64_t)(nx + 1);
+                for (int base = (int)a0; base <= nx; base += lanes) {
+                    int x = base + lane;
+                    uint32_t hits = g.ballot(x <= nx && tight_candidate(x));
+                    if (hits) {
+                        r = (uint64_t)(base + (int)ctz32(hits));
+                        break;
+                    }
+                }
+                break;
+            }
+            case OP_BLOSSOM_CLEAR:
+                k_blossom_clear(lane, lanes, (int)a0, (int)a1);
+                break;
+            case OP_MERGE_ROW:
+                k_merge_row(lane, lanes, (int)a0, (int)a1, (int)a2);
+                break;
+            case OP_PHASE_INIT:
+                k_phase_init(lane, lanes, (int)a0);
+                break;
+            default:
+                break;
+        }
+        return r;
+    }
+    // master side: announce, run together, wait for everyone's writes
+    CB_HD uint64_t call(uint32_t op, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
+        cmd[0] = op;
+        cmd[1] = a0;
+        cmd[2] = a1;
+        cmd[3] = a2;
+        g.wsync();
+        uint64_t r = dispatch(op, a0, a1, a2);
+        g.wsync();
+        return r;
+    }
+    // lanes 1..31
+    CB_HDN void worker_loop() {
+        while (true) {
+            g.wsync();
+            uint32_t op = cmd[0];
+            if (op == OP_EXIT) break;
+            dispatch(op, cmd[1], cmd[2], cmd[3]);
+            g.wsync();
+        }
+    }
+    CB_HD void release_workers() {
+        if (par) {
+            cmd[0] = OP_EXIT;
+            g.wsync();
+        }
+    }
+
+    // ---- sequential bookkeeping (master) ----
     CB_HD void update_slack(int u, int x) {
         if (!slack[x] || edist(u, x) < edist(slack[x], x)) slack[x] = (uint16_t)u;
     }
     CB_HDN void set_slack(int x) {
-        slack[x] = 0;
-        for (int u = 1; u <= n; ++u)
-            if (has(u, x) && st[u] != x && S[st[u]] == 0) update_slack(u, x);
+        uint64_t best = par ? call(OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
+        slack[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
     }
     CB_HD void q_put(int v) {
         q[qt] = (uint16_t)v;
@@ -881,19 +1092,11 @@ struct Blossom {
         }
         fl_len[b] = (uint16_t)len;
         set_st(b, b);
-        for (int x = 1; x <= n_x; ++x) geu(b, x) = geu(x, b) = 0;
-        for (int x = 1; x <= n; ++x) ffrom(b, x) = 0;
+        if (par) call(OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
+        else k_blossom_clear(0, 1, b, n_x);
         for (int i = 0; i < len; ++i) {
-            int xs = f[i];
-            for (int x = 1; x <= n_x; ++x)
-                if (has(xs, x) && (!has(b, x) || edist(xs, x) < edist(b, x))) {
-                    geu(b, x) = geu(xs, x);
-                    gev(b, x) = gev(xs, x);
-                    geu(x, b) = geu(x, xs);
-                    gev(x, b) = gev(x, xs);
-                }
-            for (int x = 1; x <= n; ++x)
-                if (ffrom(xs, x)) ffrom(b, x) = (uint16_t)xs;
+            if (par) call(OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
+            else k_merge_row(0, 1, b, f[i], n_x);
         }
         set_slack(b);
     }
@@ -944,10 +1147,8 @@ struct Blossom {
     }
     CB_HDN bool matching() {
         const int64_t INF = INT64_MAX / 4;
-        for (int x = 1; x <= n_x; ++x) {
-            S[x] = -1;
-            slack[x] = 0;
-        }
+        if (par) call(OP_PHASE_INIT, (uint32_t)n_x);
+        else k_phase_init(0, 1, n_x);
         qh = qt = 0;
         for (int x = 1; x <= n_x; ++x)
             if (st[x] == x && !match[x]) {
@@ -962,72 +1163,50 @@ struct Blossom {
                 int u = q[qh];
                 qh = qh + 1 == QC ? 0 : qh + 1;
                 if (S[st[u]] == 1) continue;
-                for (int v = 1; v <= n; ++v)
-                    if (W[u * (n + 1) + v] > 0 && st[u] != st[v]) {
-                        if (lab[u] + lab[v] - 2 * W[u * (n + 1) + v] == 0) {
-                            if (on_found_edge(u, v)) return true;
-                        } else {
-                            update_slack(u, st[v]);
+                // neighbours of u in ascending order (adjacency bit rows; W never changes during a solve)
+                for (int k = 0; k < AW; ++k) {
+                    uint32_t bits = adjm[u * AW + k];
+                    while (bits) {
+                        int v = 32 * k + (int)ctz32(bits);
+                        bits &= bits - 1;
+                        if (st[u] != st[v]) {
+                            if (lab[u] + lab[v] - 2 * W[u * (n + 1) + v] == 0) {
+                                if (on_found_edge(u, v)) return true;
+                            } else {
+                                update_slack(u, st[v]);
+                            }
                         }
                     }
+                }
             }
             if (broken) return false;
-            int64_t d = INF;
-            for (int b = n + 1; b <= n_x; ++b)
-                if (st[b] == b && S[b] == 1) d = lab[b] / 2 < d ? lab[b] / 2 : d;
-            for (int x = 1; x <= n_x; ++x)
-                if (st[x] == x && slack[x]) {
-                    int64_t sd = edist(slack[x], x);
-                    if (S[x] == -1) d = sd < d ? sd : d;
-                    else if (S[x] == 0) d = sd / 2 < d ? sd / 2 : d;
-                }
+            int64_t d = (int64_t)(par ? call(OP_DUAL_MIN, (uint32_t)n_x) : k_dual_min(0, 1, n_x));
             if (d >= INF) return false;
-            for (int u = 1; u <= n; ++u) {
-                if (S[st[u]] == 0) lab[u] -= d;
-                else if (S[st[u]] == 1) lab[u] += d;
-            }
-            for (int b = n + 1; b <= n_x; ++b)
-                if (st[b] == b) {
-                    if (S[b] == 0) lab[b] += d * 2;
-                    else if (S[b] == 1) lab[b] -= d * 2;
-                }
+            if (par) call(OP_LAB_UPDATE, (uint32_t)n_x, (uint32_t)((uint64_t)d & 0xFFFFFFFFu), (uint32_t)((uint64_t)d >> 32));
+            else k_lab_update(0, 1, n_x, d);
             qh = qt = 0;
-            for (int x = 1; x <= n_x; ++x)
-                if (st[x] == x && slack[x] && st[slack[x]] != x && edist(slack[x], x) == 0)
-                    if (on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+            if (par) {
+                for (int x = (int)call(OP_NEXT_TIGHT, 1, (uint32_t)n_x); x <= n_x; x = (int)call(OP_NEXT_TIGHT, (uint32_t)(x + 1), (uint32_t)n_x))
+                    if (tight_candidate(x) && on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+            } else {
+                for (int x = 1; x <= n_x; ++x)
+                    if (tight_candidate(x))
+                        if (on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+            }
             for (int b = n + 1; b <= n_x; ++b)
                 if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(b);
         }
     }
-    // W must be filled (symmetric, 0 = absent). Returns the number of matched pairs; match[1..n] holds partners.
+    // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match[1..n] = partners.
     CB_HDN int solve() {
         n_x = n;
         vis_t = 0;
-        for (int u = 0; u < NX; ++u) {
-            match[u] = 0;
-            st[u] = (uint16_t)(u <= n ? u : 0);
-            fl_len[u] = 0;
-            vis[u] = 0;
-            slack[u] = 0;
-            pa[u] = 0;
-            S[u] = -1;
-            lab[u] = 0;
+        if (par) {
+            call(OP_INIT);
+        } else {
+            k_init(0, 1);
+            k_set_lab(0, 1, k_wmax(0, 1));
         }
-        int64_t w_max = 0;
-        for (int u = 1; u <= n; ++u)
-            for (int v = 1; v <= n; ++v) {
-                ffrom(u, v) = (uint16_t)(u == v ? u : 0);
-                int64_t x = W[u * (n + 1) + v];
-                if (x > 0) {
-                    geu(u, v) = (uint8_t)u;
-                    gev(u, v) = (uint8_t)v;
-                } else {
-                    geu(u, v) = 0;
-                    gev(u, v) = 0;
-                }
-                if (x > w_max) w_max = x;
-            }
-        for (int u = 1; u <= n; ++u) lab[u] = w_max;
         int cnt = 0;
         while (matching()) ++cnt;
         return cnt;
@@ -1071,6 +1250,60 @@ CB_HD void request_growth(Shot &s, uint32_t ev, int64_t to) {
     s.grow_to[k] = to;
 }
 
+// Four events: the perfect-matching LP of K4 needs no blossom inequalities (an odd set of three is the complement of a
+// single vertex), so vertex duals alone certify the best of the three pairings. With the pairing {ab, cd} optimal, the
+// doubled duals h_a = t, h_b = 2 d_ab - t, h_c = s, h_d = 2 d_cd - s are feasible iff
+//     2 (d_ab + d_cd - d_bd) <= t + s <= 2 d_ac      and      2 (d_ab - d_bc) <= t - s <= 2 (d_ad - d_cd),
+// a non-empty box by optimality. The balanced point (d_ab, d_cd) is clamped into it. Returns false (generic solver)
+// when the seen edges admit no perfect matching.
+CB_HDN bool solve_component_four(Shot &s, const uint32_t *mem) {
+    int64_t d[4][4];
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) d[a][b] = -1;
+    for (int a = 0; a < 4; a++) {
+        const NbEntry *l = nb_list(s, mem[a]);
+        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++)
+            for (int b = 0; b < 4; b++)
+                if (l[k].ev == mem[b]) d[a][b] = d[b][a] = l[k].d;
+    }
+    // pairings in fixed preference order: {01,23}, {02,13}, {03,12}
+    const int pa[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
+    int best = -1;
+    int64_t best_cost = 0;
+    for (int k = 0; k < 3; k++) {
+        int64_t x = d[pa[k][0]][pa[k][1]], y = d[pa[k][2]][pa[k][3]];
+        if (x < 0 || y < 0) continue;
+        if (best < 0 || x + y < best_cost) {
+            best = k;
+            best_cost = x + y;
+        }
+    }
+    if (best < 0) return false;
+    const int A = pa[best][0], B = pa[best][1], C = pa[best][2], D = pa[best][3];
+    const int64_t dab = d[A][B], dcd = d[C][D];
+    int64_t P = dab + dcd, Q = dab - dcd;
+    if (d[A][C] >= 0 && P > 2 * d[A][C]) P = 2 * d[A][C];
+    if (d[B][D] >= 0 && P < 2 * (dab + dcd - d[B][D])) P = 2 * (dab + dcd - d[B][D]);
+    if (d[A][D] >= 0 && Q > 2 * (d[A][D] - dcd)) Q = 2 * (d[A][D] - dcd);
+    if (d[B][C] >= 0 && Q < 2 * (dab - d[B][C])) Q = 2 * (dab - d[B][C]);
+    const int64_t t = (P + Q) / 2, u = (P - Q) / 2;
+    const int64_t h[4] = {t, 2 * dab - t, u, 2 * dcd - u};
+    const int who[4] = {A, B, C, D};
+    bool ok = true;
+    for (int k = 0; k < 4; k++)
+        if (h[k] > s.R[mem[who[k]]]) {
+            request_growth(s, mem[who[k]], h[k]);
+            ok = false;
+        }
+    if (ok) {
+        s.partner[mem[A]] = (int32_t)mem[B];
+        s.partner[mem[B]] = (int32_t)mem[A];
+        s.partner[mem[C]] = (int32_t)mem[D];
+        s.partner[mem[D]] = (int32_t)mem[C];
+    }
+    return true;
+}
+
 // First pass over component c, one thread per component: sorts the members, handles odd components (everyone grows)
 // and single-edge components (closed form). Returns false when the component needs the blossom solver.
 CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
@@ -1104,25 +1337,38 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
         }
         return true;
     }
+    if (n == 4) return solve_component_four(s, mem);
     return false;
 }
 
-// Exact solve of component c by the dense blossom, on one thread. `scratch` (nullable) is fast memory the solver may
-// use when the component fits; otherwise the scratch comes from the dynamic region.
-CB_HDN void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
+// Exact solve of component c by the dense blossom; every lane of the warp calls this together. Lane 0 prepares the
+// weight matrix and drives the solver, the other lanes serve its data-parallel helpers (large components only).
+// `scratch` (nullable) is fast memory the solver may use when the component fits; otherwise the scratch comes from the
+// dynamic region.
+template <class G>
+CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
     uint32_t r = s.comp_root[c];
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
     if (n > MAX_COMPONENT) {
-        s.fail(SHOT_COMPONENT_TOO_LARGE);
+        if (g.lane == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
         return;
     }
-    uint64_t need_bytes = Blossom::bytes_needed((int)n);
-    uint8_t *memory = (scratch && need_bytes <= scratch_bytes) ? scratch : s.alloc(need_bytes);
-    if (!memory) return;
+    uint64_t need_bytes = Blossom<G>::bytes_needed((int)n);
+    uint64_t off = 0;
+    if (g.lane == 0) {
+        uint8_t *memory = (scratch && need_bytes <= scratch_bytes) ? scratch : s.alloc(need_bytes);
+        off = memory ? (uint64_t)(uintptr_t)memory : 0;
+    }
+    off = g.shfl64(off, 0);
+    if (!off) return;
+    Blossom<G> bl;
+    bl.bind((uint8_t *)(uintptr_t)off, (int)n, g);
+    if (g.lane != 0) {
+        if (bl.par) bl.worker_loop();
+        return;
+    }
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
-    Blossom bl;
-    bl.bind(memory, (int)n);
     for (uint32_t a = 0; a < n; a++) s.lidx[mem[a]] = a + 1;
     for (uint32_t k = 0; k < (n + 1) * (n + 1); k++) bl.W[k] = 0;
     int64_t big = 2;
@@ -1140,6 +1386,7 @@ CB_HDN void solve_component_blossom(Shot &s, uint32_t c, uint8_t *scratch, uint6
         }
     }
     int pairs = bl.solve();
+    bl.release_workers();
     if (s.prof) {
         int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
         cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
@@ -1197,6 +1444,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             s.hdr->mem_top = 0;
             s.hdr->ngrow = 0;
             s.hdr->nbig = 0;
+            s.hdr->nhuge = 0;
         }
         g.sync();
         for (uint32_t i = g.tid; i < M; i += g.n) {
@@ -1237,13 +1485,31 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             if (!solve_component_small(s, c)) s.root[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
         const uint32_t nbig = s.hdr->nbig;
-        // blossom components: one warp each, solved by lane 0 inside the warp's shared-memory ball tables
-        bool used_shared = false;
+        // blossom components that fit a warp's shared-memory table space: one warp each, in parallel
+        bool dirtied_shared = false;
         for (uint32_t k = g.warp; k < nbig; k += g.nwarps) {
-            if (g.lane == 0) solve_component_blossom(s, s.root[k], s.sh_ball.H ? s.sh_ball.raw : nullptr, s.sh_ball.raw_bytes);
-            used_shared = true;
+            uint32_t c = s.root[k];
+            if (s.sh_ball.H && Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[c]]) > s.sh_ball.raw_bytes && g.nwarps > 1) {
+                if (g.lane == 0) s.lidx_huge()[cb_atomic_add(&s.hdr->nhuge, 1)] = c;
+                continue;
+            }
+            solve_component_blossom(s, g, c, s.sh_ball.H ? s.sh_ball.raw : nullptr, s.sh_ball.raw_bytes);
+            g.wsync();
+            dirtied_shared = true;
         }
-        if (used_shared && s.sh_ball.H) {
+        g.sync();
+        // the few components that do not: one after the other on warp 0, in the whole block's table space
+        const uint32_t nhuge = s.hdr->nhuge;
+        if (nhuge) {
+            if (g.warp == 0)
+                for (uint32_t k = 0; k < nhuge; k++) {
+                    solve_component_blossom(s, g, s.lidx_huge()[k], s.sh_tables, s.sh_tables_bytes);
+                    g.wsync();
+                }
+            dirtied_shared = true;
+            g.sync();
+        }
+        if (dirtied_shared && s.sh_ball.H) {
             g.wsync();
             for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
         }

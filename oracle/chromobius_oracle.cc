@@ -1317,6 +1317,45 @@ struct Decoder {
         return limit;
     }
 
+    // Four events: vertex duals alone certify the best of the three pairings (K4 has no non-trivial odd-set cut).
+    // With {ab, cd} optimal the doubled duals (t, 2 d_ab - t, u, 2 d_cd - u) are feasible inside the box
+    // 2 (d_ab + d_cd - d_bd) <= t + u <= 2 d_ac,  2 (d_ab - d_bc) <= t - u <= 2 (d_ad - d_cd); the balanced point
+    // (d_ab, d_cd) is clamped into it. Returns false when the seen edges admit no perfect matching.
+    bool solve_four(const std::vector<int> &mem, const std::vector<std::vector<std::pair<int, int64_t>>> &nb, int partner[4],
+                    int64_t h[4], int64_t pdist[4]) {
+        int64_t d[4][4];
+        for (auto &row : d)
+            for (auto &x : row) x = -1;
+        for (int a = 0; a < 4; a++)
+            for (auto &p : nb[mem[a]])
+                for (int b = 0; b < 4; b++)
+                    if (p.first == mem[b]) d[a][b] = d[b][a] = p.second;
+        const int pa[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
+        int best = -1;
+        int64_t best_cost = 0;
+        for (int k = 0; k < 3; k++) {
+            int64_t x = d[pa[k][0]][pa[k][1]], y = d[pa[k][2]][pa[k][3]];
+            if (x < 0 || y < 0) continue;
+            if (best < 0 || x + y < best_cost) {
+                best = k;
+                best_cost = x + y;
+            }
+        }
+        if (best < 0) return false;
+        const int A = pa[best][0], B = pa[best][1], C = pa[best][2], D = pa[best][3];
+        const int64_t dab = d[A][B], dcd = d[C][D];
+        int64_t P = dab + dcd, Q = dab - dcd;
+        if (d[A][C] >= 0) P = std::min(P, 2 * d[A][C]);
+        if (d[B][D] >= 0) P = std::max(P, 2 * (dab + dcd - d[B][D]));
+        if (d[A][D] >= 0) Q = std::min(Q, 2 * (d[A][D] - dcd));
+        if (d[B][C] >= 0) Q = std::max(Q, 2 * (dab - d[B][C]));
+        const int64_t t = (P + Q) / 2, u = (P - Q) / 2;
+        h[A] = t; h[B] = 2 * dab - t; h[C] = u; h[D] = 2 * dcd - u;
+        partner[A] = B; partner[B] = A; partner[C] = D; partner[D] = C;
+        pdist[A] = pdist[B] = dab; pdist[C] = pdist[D] = dcd;
+        return true;
+    }
+
     // Certified local matching: the same optimum as match_events_dense without the all-pairs step, usable at
     // d25 r100 sizes. Balls grow until the blossom duals of every component fit inside them (2 y_a <= R_a), which keeps
     // the duals feasible for every pair that was never looked at; see the argument in DESIGN.md ("Matcher").
@@ -1392,6 +1431,29 @@ struct Decoder {
                         (*pdist_out)[i] = (*pdist_out)[j] = d;
                     }
                     continue;
+                }
+                if (n == 4) {
+                    int p4[4];
+                    int64_t h4[4], d4[4];
+                    if (solve_four(mem, nb, p4, h4, d4)) {
+                        bool certified = true;
+                        for (int k = 0; k < 4; k++)
+                            if (h4[k] > R[mem[k]]) certified = false;
+                        // growth requests in the order the kernel issues them: A, B, C, D of the chosen pairing
+                        int first = 0;
+                        (void)first;
+                        std::vector<int> order;
+                        for (int k = 0; k < 4; k++)
+                            if (p4[k] > k) order.push_back(k), order.push_back(p4[k]);
+                        for (int k : order)
+                            if (h4[k] > R[mem[k]]) grow.push_back({mem[k], h4[k]});
+                        if (certified)
+                            for (int k = 0; k < 4; k++) {
+                                (*partner_out)[mem[k]] = mem[p4[k]];
+                                (*pdist_out)[mem[k]] = d4[k];
+                            }
+                        continue;
+                    }
                 }
                 stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
                 std::vector<int> &loc = loc_buf;
