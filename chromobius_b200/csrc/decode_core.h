@@ -56,7 +56,11 @@ enum ShotStatus : uint32_t {
     SHOT_COMPONENT_TOO_LARGE = 6,   // a matching component exceeded MAX_COMPONENT events
 };
 
-constexpr uint32_t MAX_COMPONENT = 250;  // endpoints are stored as u8 in the blossom's edge matrix
+constexpr uint32_t MAX_COMPONENT = 2000;      // larger matching components are reported, not decoded
+#ifndef CB_NARROW_COMPONENT
+#define CB_NARROW_COMPONENT 250
+#endif
+constexpr uint32_t NARROW_COMPONENT = CB_NARROW_COMPONENT;  // up to here the blossom's edge matrix stores endpoints as u8, beyond as u16
 constexpr uint32_t MAX_ROUNDS = 64;
 constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t FRONT_CLOSED = 0xFFFFFFFFu;
@@ -206,7 +210,8 @@ struct BallTables {
     int64_t *dist;     // [H]
     uint32_t *fpos;    // [H] position in `front`, FRONT_CLOSED once settled
     uint32_t *used;    // [cap] slots in insertion order (O(touched) clean-up)
-    uint64_t *front;   // [cap] open nodes as (distance << 20 | slot): the minimum is the next node to settle
+    uint64_t *front;   // [cap] open nodes as (distance << 24 | node): the minimum is the next node to settle, so the
+                       // settling order is (distance, node id) -- independent of table size and lane count
     NbEntry *found;    // [fcap]
     uint32_t H, cap, fcap;
     uint32_t nused, nfront;
@@ -519,7 +524,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
         dist[k] = 0;
         fpos[k] = 0;
         used[0] = k;
-        front[0] = k;
+        front[0] = src;
     }
     g.wsync();
     uint32_t nfound = 0;
@@ -533,16 +538,19 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
             best = cand < best ? cand : best;
         }
         best = g.min64(best);
-        const int64_t d = (int64_t)(best >> 20);
-        const uint32_t slot = (uint32_t)(best & 0xFFFFF);
+        const int64_t d = (int64_t)(best >> 24);
+        const uint32_t u = (uint32_t)(best & 0xFFFFFF);
         if (limit >= 0 && (inclusive ? d > limit : d >= limit)) break;
-        const uint32_t u = key[slot];
+        uint32_t slot = ht_hash(u, H);
+        while (key[slot] != u) slot = (slot + 1) & hmask;
         const uint32_t q = fpos[slot];
         g.wsync();
         if (lane == 0) {
             uint64_t last = front[nfront - 1];
             front[q] = last;
-            fpos[(uint32_t)(last & 0xFFFFF)] = q;
+            uint32_t ls = ht_hash((uint32_t)(last & 0xFFFFFF), H);
+            while (key[ls] != (uint32_t)(last & 0xFFFFFF)) ls = (ls + 1) & hmask;
+            fpos[ls] = q;
             fpos[slot] = FRONT_CLOSED;
         }
         nfront--;
@@ -582,13 +590,15 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
         }
         for (uint32_t base = e0; base < e1; base += lanes) {
             const uint32_t e = base + lane;
-            bool is_new = false;
-            uint32_t my_slot = 0;
+            bool is_new = false, too_far = false;
+            uint32_t my_slot = 0, my_node = 0;
             int64_t nd = 0;
             if (e < e1) {
                 AdjEntry a = adj[e];
                 nd = d + a.wt;
+                my_node = a.nbr;
                 if (a.nbr != NO_INDEX && !(limit >= 0 && (inclusive ? nd > limit : nd >= limit))) {
+                    too_far = nd >= (int64_t{1} << 39);  // frontier keys hold 40 distance bits
                     uint32_t k = ht_hash(a.nbr, H);
                     while (true) {
                         uint32_t old = cb_atomic_cas(&key[k], HT_EMPTY, a.nbr);
@@ -606,7 +616,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
                         uint32_t fp = fpos[k];
                         if (fp != FRONT_CLOSED && nd < dist[k]) {
                             dist[k] = nd;
-                            front[fp] = ((uint64_t)nd << 20) | k;
+                            front[fp] = ((uint64_t)nd << 24) | a.nbr;
                         }
                     }
                 }
@@ -615,14 +625,16 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
             if (is_new) {
                 uint32_t idx = popc32(fresh & lane_lt);
                 used[nused + idx] = my_slot;
-                front[nfront + idx] = ((uint64_t)nd << 20) | my_slot;
+                front[nfront + idx] = ((uint64_t)nd << 24) | my_node;
                 fpos[my_slot] = nfront + idx;
             }
             const uint32_t c = popc32(fresh);
             nused += c;
             nfront += c;
             g.wsync();
+            if (g.ballot(too_far)) result = BALL_OVERFLOW;
         }
+        if (result != BALL_OK) break;
     }
     t.nused = nused;
     t.nfront = nfront;
@@ -716,6 +728,7 @@ struct Blossom {
     uint32_t vis_t;
     bool broken;
     bool par;
+    bool wide;         // endpoints stored as u16
     G g;
 
     static CB_HD uint64_t bytes_needed(int n) {
@@ -724,7 +737,7 @@ struct Blossom {
         int AW = (n + 32) / 32;
         uint64_t b = 0;
         b += align16(uint64_t(n + 1) * (n + 1) * 8);
-        b += align16(uint64_t(NX) * NX * 2);
+        b += align16(uint64_t(NX) * NX * 2 * (n > (int)NARROW_COMPONENT ? 2 : 1));
         b += align16(uint64_t(NX) * 8);
         b += align16(uint64_t(NX) * 2) * 4;
         b += align16(uint64_t(NX));
@@ -746,8 +759,9 @@ struct Blossom {
         QC = 2 * n + 4;
         AW = (n + 32) / 32;
         uint8_t *p = mem;
+        wide = n > (int)NARROW_COMPONENT;
         W = (int64_t *)p; p += align16(uint64_t(n + 1) * (n + 1) * 8);
-        ge = p; p += align16(uint64_t(NX) * NX * 2);
+        ge = p; p += align16(uint64_t(NX) * NX * 2 * (wide ? 2 : 1));
         lab = (int64_t *)p; p += align16(uint64_t(NX) * 8);
         match = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
         slack = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
@@ -767,9 +781,18 @@ struct Blossom {
         n_x = n;
     }
     CB_HD int64_t &w(int u, int v) { return W[u * (n + 1) + v]; }
-    CB_HD uint8_t &geu(int a, int b) { return ge[(a * NX + b) * 2]; }
-    CB_HD uint8_t &gev(int a, int b) { return ge[(a * NX + b) * 2 + 1]; }
-    CB_HD bool has(int a, int b) { return ge[(a * NX + b) * 2] != 0; }
+    CB_HD int geu(int a, int b) const { return wide ? ((const uint16_t *)ge)[(a * NX + b) * 2] : ge[(a * NX + b) * 2]; }
+    CB_HD int gev(int a, int b) const { return wide ? ((const uint16_t *)ge)[(a * NX + b) * 2 + 1] : ge[(a * NX + b) * 2 + 1]; }
+    CB_HD bool has(int a, int b) const { return geu(a, b) != 0; }
+    CB_HD void set_ge(int a, int b, int eu, int ev) {
+        if (wide) {
+            ((uint16_t *)ge)[(a * NX + b) * 2] = (uint16_t)eu;
+            ((uint16_t *)ge)[(a * NX + b) * 2 + 1] = (uint16_t)ev;
+        } else {
+            ge[(a * NX + b) * 2] = (uint8_t)eu;
+            ge[(a * NX + b) * 2 + 1] = (uint8_t)ev;
+        }
+    }
     CB_HD int64_t edist(int a, int b) {  // slack of the best edge between nodes a and b
         int eu = geu(a, b), ev = gev(a, b);
         return lab[eu] + lab[ev] - 2 * W[eu * (n + 1) + ev];
@@ -795,12 +818,10 @@ struct Blossom {
                 ffrom(u, v) = (uint16_t)(u == v ? u : 0);
                 int64_t x = W[u * (n + 1) + v];
                 if (x > 0) {
-                    geu(u, v) = (uint8_t)u;
-                    gev(u, v) = (uint8_t)v;
+                    set_ge(u, v, u, v);
                     adjm[u * AW + (v >> 5)] |= 1u << (v & 31);
                 } else {
-                    geu(u, v) = 0;
-                    gev(u, v) = 0;
+                    set_ge(u, v, 0, 0);
                 }
             }
         }
@@ -861,16 +882,17 @@ struct Blossom {
         return st[x] == x && slack[x] && st[slack[x]] != x && edist(slack[x], x) == 0;
     }
     CB_HD void k_blossom_clear(int lane, int lanes, int b, int nx) {
-        for (int x = 1 + lane; x <= nx; x += lanes) geu(b, x) = geu(x, b) = 0;
+        for (int x = 1 + lane; x <= nx; x += lanes) {
+            set_ge(b, x, 0, 0);
+            set_ge(x, b, 0, 0);
+        }
         for (int x = 1 + lane; x <= n; x += lanes) ffrom(b, x) = 0;
     }
     CB_HD void k_merge_row(int lane, int lanes, int b, int xs, int nx) {
         for (int x = 1 + lane; x <= nx; x += lanes)
             if (has(xs, x) && (!has(b, x) || edist(xs, x) < edist(b, x))) {
-                geu(b, x) = geu(xs, x);
-                gev(b, x) = gev(xs, x);
-                geu(x, b) = geu(x, xs);
-                gev(x, b) = gev(x, xs);
+                set_ge(b, x, geu(xs, x), gev(xs, x));
+                set_ge(x, b, geu(x, xs), gev(x, xs));
             }
         for (int x = 1 + lane; x <= n; x += lanes)
             if (ffrom(xs, x)) ffrom(b, x) = (uint16_t)xs;
@@ -1029,7 +1051,7 @@ struct Blossom {
         while (sp) {
             int v = stk[--sp];
             int u = stk[--sp];
-            match[u] = gev(u, v);
+            match[u] = (uint16_t)gev(u, v);
             if (u <= n) continue;
             int eu = geu(u, v);
             int xr = ffrom(u, eu);
@@ -1108,7 +1130,7 @@ struct Blossom {
         int pr = get_pr(b, xr);
         for (int i = 0; i < pr; i += 2) {
             int xs = f[i], xns = f[i + 1];
-            pa[xs] = geu(xns, xs);
+            pa[xs] = (uint16_t)geu(xns, xs);
             S[xs] = 1;
             S[xns] = 0;
             slack[xs] = 0;

@@ -858,6 +858,8 @@ const char *charge_name(unsigned c) {
 HostTables compile_tables(const FlatDem &dem) {
     HostTables t;
     if (dem.num_detectors > 0x7FFFFFFEull) fail("The detector error model is too large.");
+    if (dem.num_detectors * 2 > (1ull << 24))
+        fail("The detector error model is too large: the B200 matcher supports at most 2^23 detectors.");
     t.num_dets = (uint32_t)dem.num_detectors;
     t.num_obs = (uint32_t)dem.num_observables;
     Ctx cx(dem, t);

@@ -57,6 +57,7 @@ def lib():
         L.orc_lift_edges.argtypes = [vp, vp, vp, u64, vp]
         L.orc_set_matcher_mode.argtypes = [vp, ctypes.c_int]
         L.orc_matcher_stats.argtypes = [vp, vp, ctypes.c_int]
+        L.orc_set_odd_policy.argtypes = [vp, ctypes.c_int]
         L.orc_match_events.restype = i64
         L.orc_match_events.argtypes = [vp, vp, u64, vp, vp]
         _lib = L
@@ -87,11 +88,14 @@ class OracleDecoder:
         """0: dense all-pairs matcher up to 160 events, certified-local beyond; 1: always local; 2: always dense."""
         lib().orc_set_matcher_mode(self._h, int(mode))
 
+    def set_odd_policy(self, policy):
+        lib().orc_set_odd_policy(self._h, int(policy))
+
     def matcher_stats(self, reset=True):
-        out = np.zeros(6, np.uint64)
+        out = np.zeros(7, np.uint64)
         lib().orc_matcher_stats(self._h, _ptr(out), 1 if reset else 0)
         return dict(blossoms_le8=int(out[0]), blossoms_le16=int(out[1]), blossoms_le32=int(out[2]), blossoms_gt32=int(out[3]),
-                    rounds=int(out[4]), closed_form_pairs=int(out[5]))
+                    rounds=int(out[4]), closed_form_pairs=int(out[5]), max_component=int(out[6]))
 
     def clone(self):
         return OracleDecoder(None, _handle=lib().orc_clone(self._h))

@@ -1111,6 +1111,7 @@ struct Decoder {
     uint64_t stat_radius_retries = 0;
     // 0 = dense all-pairs matcher up to 160 events, local beyond; 1 = always local; 2 = always dense
     int matcher_mode = 0;
+    int odd_policy = 0;  // 0: every member of an odd component grows; 1: only the vertices a maximum matching leaves exposed
     DenseBlossom local_blossom;
     std::vector<int> loc_buf;
 
@@ -1407,7 +1408,7 @@ struct Decoder {
                 for (int i : mem) is_dirty |= dirty[i] != 0;
                 if (!is_dirty) continue;
                 int n = (int)mem.size();
-                if (n % 2) {
+                if (n % 2 && (odd_policy == 0 || n == 1)) {
                     for (int i : mem) grow.push_back({i, -1});
                     continue;
                 }
@@ -1432,7 +1433,7 @@ struct Decoder {
                     }
                     continue;
                 }
-                if (n == 4) {
+                if (n == 4 && odd_policy != 99) {
                     int p4[4];
                     int64_t h4[4], d4[4];
                     if (solve_four(mem, nb, p4, h4, d4)) {
@@ -1456,6 +1457,7 @@ struct Decoder {
                     }
                 }
                 stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
+                stat_max_comp = std::max<uint64_t>(stat_max_comp, (uint64_t)n);
                 std::vector<int> &loc = loc_buf;
                 loc.resize(m);
                 for (int k = 0; k < n; k++) loc[mem[k]] = k + 1;
@@ -1511,7 +1513,7 @@ struct Decoder {
     // Final state: every event solved, h_a <= R_a for all a (covers unseen pairs) and h_a + h_b <= 2 d(a, b) for every
     // seen pair in different components, so the union of the component matchings is a global optimum.
     uint64_t stat_blossoms[4] = {0, 0, 0, 0};  // component sizes <= 8, <= 16, <= 32, > 32
-    uint64_t stat_rounds = 0, stat_pairs_closed_form = 0;
+    uint64_t stat_rounds = 0, stat_pairs_closed_form = 0, stat_max_comp = 0;
     bool match_events_lazy(const std::vector<uint64_t> &events, std::vector<int> *partner_out, std::vector<int64_t> *pdist_out) {
         int m = (int)events.size();
         partner_out->assign(m, -1);
@@ -1604,6 +1606,7 @@ struct Decoder {
                     continue;
                 }
                 stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
+                stat_max_comp = std::max<uint64_t>(stat_max_comp, (uint64_t)n);
                 std::vector<int> &loc = loc_buf;
                 loc.resize(m);
                 for (int k = 0; k < n; k++) loc[mem[k]] = k + 1;
@@ -1902,14 +1905,16 @@ double orc_normalising_constant(void *h) { return ((Decoder *)h)->t->normalising
 uint64_t orc_drag_ambiguities(void *h) { return ((Decoder *)h)->t->drag_ambiguities; }
 uint64_t orc_radius_retries(void *h) { return ((Decoder *)h)->stat_radius_retries; }
 void orc_set_matcher_mode(void *h, int mode) { ((Decoder *)h)->matcher_mode = mode; }
-void orc_matcher_stats(void *h, uint64_t *out6, int reset) {
+void orc_set_odd_policy(void *h, int p) { ((Decoder *)h)->odd_policy = p; }
+void orc_matcher_stats(void *h, uint64_t *out6 /* 7 values */, int reset) {
     auto *d = (Decoder *)h;
     for (int k = 0; k < 4; k++) out6[k] = d->stat_blossoms[k];
     out6[4] = d->stat_rounds;
     out6[5] = d->stat_pairs_closed_form;
+    out6[6] = d->stat_max_comp;
     if (reset) {
         for (int k = 0; k < 4; k++) d->stat_blossoms[k] = 0;
-        d->stat_rounds = d->stat_pairs_closed_form = 0;
+        d->stat_rounds = d->stat_pairs_closed_form = d->stat_max_comp = 0;
     }
 }
 

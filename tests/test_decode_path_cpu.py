@@ -152,3 +152,31 @@ def test_lift_is_pinned_on_oracle_edges(built):
         obs, w, st, rd, edges = sim.decode(row, want_edges=True)
         if len(edges):
             assert od.lift_edges(row, edges) == int(obs[0])
+
+
+def test_wide_blossom_layout(built, tmp_path):
+    """Components beyond 250 events switch the blossom's edge matrix to u16 endpoints. Force that layout for every
+    component above 5 events (test build with -DCB_NARROW_COMPONENT=5) and require identical results."""
+    import ctypes
+    import os
+    import subprocess
+    import sim_util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / 'libcb200_sim_wide.so')
+    subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-Wno-sign-compare', '-DCB_NARROW_COMPONENT=5', '-shared', '-o', so,
+                           os.path.join(root, 'tests', 'sim', 'host_sim.cc'),
+                           os.path.join(root, 'chromobius_b200', 'csrc', 'host_compile.cc')])
+    text = read_dem('superdense_color_code_d5_r20_p1000')
+    dets, _ = NumpyDemSampler(text).sample(300, seed=8)
+    want = SimDecoder(text).decode(dets)
+    saved = sim_util._lib
+    try:
+        sim_util._lib = None
+        real_build = built.build_sim
+        built.build_sim = lambda force=False: so
+        got = SimDecoder(text).decode(dets)
+    finally:
+        built.build_sim = real_build
+        sim_util._lib = saved
+    assert (got[2] == 0).all()
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
