@@ -95,7 +95,7 @@ def _cpu_worker(args):
     dem_text, dets = args
     import oracle
     dec = oracle.OracleDecoder(dem_text)
-    dec.set_matcher_mode(1)
+    dec.set_matcher_mode(3)
     t0 = time.monotonic()
     obs, w = dec.decode_batch(dets)
     return time.monotonic() - t0, int(w.sum() & 0xFFFFFFFF)

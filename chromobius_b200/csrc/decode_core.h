@@ -246,9 +246,9 @@ CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t f
 // Per-event arrays (all sized max_events), see struct Shot.
 CB_HD uint64_t event_bytes(const ScratchConfig &c) {
     uint64_t m = c.max_events;
-    // evdet(u32) R(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) + 9 x u32 + 3 x u8
-    return align16(m * 4) + align16(m * 8) + align16(m * 4) * 2 + align16(m * 4) + align16(m * 8) + align16(m * 4) +
-           align16(m * 4) * 9 + align16(m) * 3;
+    // evdet(u32) R(i64) h(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) + 10 x u32 + 5 x u8
+    return align16(m * 4) + align16(m * 8) * 2 + align16(m * 4) * 2 + align16(m * 4) + align16(m * 8) + align16(m * 4) +
+           align16(m * 4) * 10 + align16(m) * 5;
 }
 CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets, uint32_t nwarps) {
     uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
@@ -277,13 +277,18 @@ struct Shot {
     uint32_t M;            // matcher events = 2 * detection events
     // per event
     uint32_t *evdet;       // [M/2] ascending detector ids
-    int64_t *R;            // explored radius
+    int64_t *R;            // explored (open) ball radius
+    int64_t *h;            // doubled dual of a solved event (h_a = 2 y_a)
     uint32_t *nb_off, *nb_cnt;
     uint32_t *grow_ev;
     int64_t *grow_to;
     int32_t *partner;
     uint32_t *uf, *root, *cnt, *start, *fillp, *members, *lidx, *comp_root, *path_off, *path_len;
-    uint8_t *dirty, *comp_dirty, *used_flag;
+    uint32_t *pc;          // solved events: smallest member of the component they were last solved in
+    uint8_t *solved;       // the event holds a partner and a dual from a perfect solve of its component
+    uint8_t *regrown;      // the ball grew since the component was last looked at
+    uint8_t *stale;        // indexed by pc: a member's new ball shows a violated pair inside the solved component
+    uint8_t *comp_dirty, *used_flag;
     // dynamic region
     uint8_t *dyn;
     uint64_t dyn_cap;
@@ -329,15 +334,18 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     uint64_t m = p.cfg.max_events;
     s.evdet = (uint32_t *)q; q += align16(m * 4);
     s.R = (int64_t *)q; q += align16(m * 8);
+    s.h = (int64_t *)q; q += align16(m * 8);
     s.nb_off = (uint32_t *)q; q += align16(m * 4);
     s.nb_cnt = (uint32_t *)q; q += align16(m * 4);
     s.grow_ev = (uint32_t *)q; q += align16(m * 4);
     s.grow_to = (int64_t *)q; q += align16(m * 8);
     s.partner = (int32_t *)q; q += align16(m * 4);
-    uint32_t **arrs[] = {&s.uf, &s.root, &s.cnt, &s.start, &s.fillp, &s.members, &s.lidx, &s.comp_root, &s.path_off};
+    uint32_t **arrs[] = {&s.uf, &s.root, &s.cnt, &s.start, &s.fillp, &s.members, &s.lidx, &s.comp_root, &s.path_off, &s.pc};
     for (auto a : arrs) { *a = (uint32_t *)q; q += align16(m * 4); }
     s.path_len = s.fillp;  // fillp is dead once the matcher has finished; path_len is only used afterwards
-    s.dirty = q; q += align16(m);
+    s.solved = q; q += align16(m);
+    s.regrown = q; q += align16(m);
+    s.stale = q; q += align16(m);
     s.comp_dirty = q; q += align16(m);
     s.used_flag = q; q += align16(m);
     s.dyn = q;
@@ -646,7 +654,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
 
 CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry *)(s.dyn + ((uint64_t)s.nb_off[i] << 4)); }
 
-// Grows the ball of event i (one warp). Writes nb_off/nb_cnt/R of event i and marks i and every reported event dirty.
+// Grows the ball of event i (one warp). Writes nb_off/nb_cnt/R of event i and flags it as regrown.
 template <class G>
 CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
     const uint32_t src = s.event_node(i);
@@ -678,12 +686,10 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
     if (!off) return;
     NbEntry *dst = (NbEntry *)(s.dyn + (off - 1));
     for (uint32_t k = g.lane; k < nfound; k += g.lanes) {
-        NbEntry e = t->found[k];
-        dst[k] = e;
-        s.dirty[e.ev] = 1;
+        dst[k] = t->found[k];
     }
     if (g.lane == 0) {
-        s.dirty[i] = 1;
+        s.regrown[i] = 1;
         s.nb_off[i] = (uint32_t)((off - 1) >> 4);
         s.nb_cnt[i] = nfound;
         s.R[i] = limit;
@@ -1311,18 +1317,17 @@ CB_HDN bool solve_component_four(Shot &s, const uint32_t *mem) {
     const int64_t t = (P + Q) / 2, u = (P - Q) / 2;
     const int64_t h[4] = {t, 2 * dab - t, u, 2 * dcd - u};
     const int who[4] = {A, B, C, D};
-    bool ok = true;
-    for (int k = 0; k < 4; k++)
-        if (h[k] > s.R[mem[who[k]]]) {
-            request_growth(s, mem[who[k]], h[k]);
-            ok = false;
-        }
-    if (ok) {
-        s.partner[mem[A]] = (int32_t)mem[B];
-        s.partner[mem[B]] = (int32_t)mem[A];
-        s.partner[mem[C]] = (int32_t)mem[D];
-        s.partner[mem[D]] = (int32_t)mem[C];
+    for (int k = 0; k < 4; k++) {
+        uint32_t e = mem[who[k]];
+        s.h[e] = h[k];
+        s.solved[e] = 1;
+        s.pc[e] = mem[0];
+        if (h[k] > s.R[e]) request_growth(s, e, h[k]);
     }
+    s.partner[mem[A]] = (int32_t)mem[B];
+    s.partner[mem[B]] = (int32_t)mem[A];
+    s.partner[mem[C]] = (int32_t)mem[D];
+    s.partner[mem[D]] = (int32_t)mem[C];
     return true;
 }
 
@@ -1343,20 +1348,24 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
         mem[b] = v;
     }
     if (n & 1) {
-        for (uint32_t a = 0; a < n; a++) request_growth(s, mem[a], -1);
+        // nobody can be left over: every member looks further
+        for (uint32_t a = 0; a < n; a++) {
+            s.solved[mem[a]] = 0;
+            request_growth(s, mem[a], -1);
+        }
         return true;
     }
     if (n == 2) {
         // Closed form of the blossom on one edge: y = d/2 each, so both balls need radius >= d.
         uint32_t i = mem[0], j = mem[1];
         int64_t d = seen_distance(s, i, j);
-        bool ok = true;
-        if (d > s.R[i]) { request_growth(s, i, d); ok = false; }
-        if (d > s.R[j]) { request_growth(s, j, d); ok = false; }
-        if (ok) {
-            s.partner[i] = (int32_t)j;
-            s.partner[j] = (int32_t)i;
-        }
+        s.h[i] = s.h[j] = d;
+        s.solved[i] = s.solved[j] = 1;
+        s.pc[i] = s.pc[j] = i;
+        s.partner[i] = (int32_t)j;
+        s.partner[j] = (int32_t)i;
+        if (d > s.R[i]) request_growth(s, i, d);
+        if (d > s.R[j]) request_growth(s, j, d);
         return true;
     }
     if (n == 4) return solve_component_four(s, mem);
@@ -1393,15 +1402,17 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     for (uint32_t a = 0; a < n; a++) s.lidx[mem[a]] = a + 1;
     for (uint32_t k = 0; k < (n + 1) * (n + 1); k++) bl.W[k] = 0;
+    // only pairs inside the component take part; pairs seen across components are guarded by the dual check
     int64_t big = 2;
     for (uint32_t a = 0; a < n; a++) {
         const NbEntry *l = nb_list(s, mem[a]);
         for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++)
-            if (l[k].d + 2 > big) big = l[k].d + 2;
+            if (s.root[l[k].ev] == r && l[k].d + 2 > big) big = l[k].d + 2;
     }
     for (uint32_t a = 0; a < n; a++) {
         const NbEntry *l = nb_list(s, mem[a]);
         for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++) {
+            if (s.root[l[k].ev] != r) continue;
             uint32_t b = s.lidx[l[k].ev];
             bl.w((int)a + 1, (int)b) = big - l[k].d;
             bl.w((int)b, (int)a + 1) = big - l[k].d;
@@ -1419,20 +1430,21 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
         return;
     }
     if ((uint32_t)pairs * 2 != n) {
-        for (uint32_t a = 0; a < n; a++)
+        for (uint32_t a = 0; a < n; a++) {
+            s.solved[mem[a]] = 0;
             if (!bl.match[a + 1]) request_growth(s, mem[a], -1);
+        }
         return;
     }
-    bool ok = true;
     for (uint32_t a = 0; a < n; a++) {
+        uint32_t e = mem[a];
         int64_t need = big - bl.lab[a + 1];  // = 2 * y_a
-        if (need > s.R[mem[a]]) {
-            request_growth(s, mem[a], need);
-            ok = false;
-        }
+        s.h[e] = need;
+        s.solved[e] = 1;
+        s.pc[e] = mem[0];
+        s.partner[e] = (int32_t)mem[bl.match[a + 1] - 1];
+        if (need > s.R[e]) request_growth(s, e, need);
     }
-    if (ok)
-        for (uint32_t a = 0; a < n; a++) s.partner[mem[a]] = (int32_t)mem[bl.match[a + 1] - 1];
 }
 
 template <class G>
@@ -1440,7 +1452,10 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     const uint32_t M = s.M;
     for (uint32_t i = g.tid; i < M; i += g.n) {
         s.partner[i] = -1;
-        s.dirty[i] = 0;
+        s.solved[i] = 0;
+        s.regrown[i] = 0;
+        s.stale[i] = 0;
+        s.pc[i] = NO_INDEX;
         s.nb_cnt[i] = 0;
         s.used_flag[i] = 0;
     }
@@ -1469,15 +1484,29 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             s.hdr->nhuge = 0;
         }
         g.sync();
+        // Lazy merging: a solved component stays whole; two events are joined when either has no dual yet or their duals
+        // overlap (h_i + h_j > 2 d). A violated pair inside one solved component is either an old blossom-internal edge or a
+        // pair first seen after the solve -- only a ball that grew since can show the latter, which marks it stale.
         for (uint32_t i = g.tid; i < M; i += g.n) {
+            const bool si = s.solved[i] != 0;
+            if (si) uf_union(s.uf, i, s.pc[i]);
             const NbEntry *l = nb_list(s, i);
-            for (uint32_t k = 0; k < s.nb_cnt[i]; k++) uf_union(s.uf, i, l[k].ev);
+            for (uint32_t k = 0; k < s.nb_cnt[i]; k++) {
+                uint32_t j = l[k].ev;
+                if (!si || !s.solved[j] || s.h[i] + s.h[j] > 2 * l[k].d) {
+                    if (si && s.solved[j] && s.pc[i] == s.pc[j] && s.regrown[i]) s.stale[s.pc[i]] = 1;
+                    uf_union(s.uf, i, j);
+                }
+            }
         }
         g.sync();
         for (uint32_t i = g.tid; i < M; i += g.n) {
             uint32_t r = uf_find(s.uf, i);
             s.root[i] = r;
-            if (s.dirty[i]) s.comp_dirty[r] = 1;
+            s.regrown[i] = 0;
+            // a component is (re)solved when a member has no dual, when it joins events of different solved components,
+            // or when a solved component went stale
+            if (!s.solved[i] || s.stale[s.pc[i]] || !s.solved[r] || s.pc[r] != s.pc[i]) s.comp_dirty[r] = 1;
         }
         g.sync();
         for (uint32_t i = g.tid; i < M; i += g.n)
@@ -1496,21 +1525,21 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             if (s.comp_dirty[r]) {
                 uint32_t p = cb_atomic_add(&s.fillp[r], 1);
                 s.members[s.start[r] + p] = i;
+                if (s.solved[i]) s.stale[s.pc[i]] = 0;
             }
-            s.dirty[i] = 0;
         }
         g.sync();
         const uint32_t ncomp = s.hdr->ncomp;
         pt.lap(2);
-        // small components: one thread each; the rest is queued for the blossom (s.root is free again: queue)
+        // small components: one thread each; the rest is queued for the blossom (s.uf is free until the next round)
         for (uint32_t c = g.tid; c < ncomp; c += g.n)
-            if (!solve_component_small(s, c)) s.root[cb_atomic_add(&s.hdr->nbig, 1)] = c;
+            if (!solve_component_small(s, c)) s.uf[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
         const uint32_t nbig = s.hdr->nbig;
         // blossom components that fit a warp's shared-memory table space: one warp each, in parallel
         bool dirtied_shared = false;
         for (uint32_t k = g.warp; k < nbig; k += g.nwarps) {
-            uint32_t c = s.root[k];
+            uint32_t c = s.uf[k];
             if (s.sh_ball.H && Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[c]]) > s.sh_ball.raw_bytes && g.nwarps > 1) {
                 if (g.lane == 0) s.lidx_huge()[cb_atomic_add(&s.hdr->nhuge, 1)] = c;
                 continue;

@@ -85,7 +85,8 @@ class OracleDecoder:
         self.normalising_constant = L.orc_normalising_constant(self._h)
 
     def set_matcher_mode(self, mode):
-        """0: dense all-pairs matcher up to 160 events, certified-local beyond; 1: always local; 2: always dense."""
+        """0: dense all-pairs matcher up to 160 events, certified-local (lazy merging) beyond; 1: certified-local with eager
+        merging; 2: always dense; 3: always certified-local with lazy merging (the algorithm the kernels run)."""
         lib().orc_set_matcher_mode(self._h, int(mode))
 
     def set_odd_policy(self, policy):

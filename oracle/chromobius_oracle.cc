@@ -1109,7 +1109,8 @@ struct Decoder {
     std::string last_error;
     // statistics
     uint64_t stat_radius_retries = 0;
-    // 0 = dense all-pairs matcher up to 160 events, local beyond; 1 = always local; 2 = always dense
+    // 0 = dense all-pairs matcher up to 160 events, certified-local with lazy merging beyond; 1 = certified-local, eager
+    // merging; 2 = always dense; 3 = always certified-local with lazy merging (the kernels' algorithm)
     int matcher_mode = 0;
     int odd_policy = 0;  // 0: every member of an odd component grows; 1: only the vertices a maximum matching leaves exposed
     DenseBlossom local_blossom;
@@ -1204,10 +1205,10 @@ struct Decoder {
         int m = (int)events.size();
         if (m == 0) return true;
         if (matcher_mode == 1 || matcher_mode == 3 || (matcher_mode == 0 && m > 160)) {
+            const bool lazy = matcher_mode != 1;
             std::vector<int> partner;
             std::vector<int64_t> pdist;
-            if (matcher_mode == 3 ? !match_events_lazy(events, &partner, &pdist) : !match_events_local(events, &partner, &pdist))
-                return false;
+            if (lazy ? !match_events_lazy(events, &partner, &pdist) : !match_events_local(events, &partner, &pdist)) return false;
             for (int i = 0; i < m; i++) {
                 int j = partner[i];
                 if (j > i) {
@@ -1604,6 +1605,25 @@ struct Decoder {
                     (*partner_out)[j] = i;
                     (*pdist_out)[i] = (*pdist_out)[j] = d;
                     continue;
+                }
+                if (n == 4) {
+                    int p4[4];
+                    int64_t h4[4], d4[4];
+                    if (solve_four(mem, nb, p4, h4, d4)) {
+                        std::vector<int> order;
+                        for (int k = 0; k < 4; k++)
+                            if (p4[k] > k) order.push_back(k), order.push_back(p4[k]);
+                        for (int k : order) {
+                            int e = mem[k];
+                            h[e] = h4[k];
+                            solved[e] = 1;
+                            pc[e] = mem[0];
+                            (*partner_out)[e] = mem[p4[k]];
+                            (*pdist_out)[e] = d4[k];
+                            if (h4[k] > R[e]) grow.push_back({e, h4[k]});
+                        }
+                        continue;
+                    }
                 }
                 stat_blossoms[n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))]++;
                 stat_max_comp = std::max<uint64_t>(stat_max_comp, (uint64_t)n);
