@@ -23,7 +23,7 @@ import numpy as np
 __version__ = '1.2.dev0+b200'
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, 'libchromobius_b200.so')
+_LIB_PATH = os.environ.get('CHROMOBIUS_B200_LIB') or os.path.join(_HERE, 'libchromobius_b200.so')  # env: A/B builds
 _lib = None
 
 CB200_IO_HOST = 0

@@ -53,13 +53,22 @@ struct DevGroup {
     __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) const {
         return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, src);
     }
+    // 64-bit warp minimum from two 32-bit hardware reductions (REDUX): high words first, then the low words of the
+    // lanes that tie on the high word.
     __device__ __forceinline__ uint64_t min64(uint64_t v) const {
+#ifdef CB_NO_REDUX
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             uint64_t w = (uint64_t)__shfl_xor_sync(0xFFFFFFFFu, (unsigned long long)v, o);
             v = w < v ? w : v;
         }
         return v;
+#endif
+        const uint32_t hi = (uint32_t)(v >> 32);
+        const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+        const uint32_t lo = hi == mh ? (uint32_t)v : 0xFFFFFFFFu;
+        const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, lo);
+        return ((uint64_t)mh << 32) | ml;
     }
 };
 
@@ -363,7 +372,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 8;
     uint32_t gl = std::min<uint32_t>(full, 13 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
-    pl.cfg.sh_found = 24;
+    pl.cfg.sh_found = 16;
     pl.cfg.ht_log2 = gl;
     pl.cfg.found_cap = 256u << (2 * escalation);
     pl.cfg.max_events = std::max<uint32_t>(2 * max_det_events, 2);

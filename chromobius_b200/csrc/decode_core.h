@@ -212,6 +212,7 @@ struct BallTables {
     uint32_t *used;    // [cap] slots in insertion order (O(touched) clean-up)
     uint64_t *front;   // [cap] open nodes as (distance << 24 | node): the minimum is the next node to settle, so the
                        // settling order is (distance, node id) -- independent of table size and lane count
+    uint32_t *fslot;   // [cap] hash slot of every open node (parallel to front)
     NbEntry *found;    // [fcap]
     uint32_t H, cap, fcap;
     uint32_t nused, nfront;
@@ -223,7 +224,7 @@ CB_HD uint64_t ball_table_bytes(uint32_t log2, uint32_t fcap) {
     if (log2 == 0) return 0;
     uint64_t H = uint64_t{1} << log2;
     uint64_t cap = H * 3 / 4;
-    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(cap * 4) + align16(cap * 8) +
+    return align16(H * 4) + align16(H * 8) + align16(H * 4) + align16(cap * 4) * 2 + align16(cap * 8) +
            align16(uint64_t{fcap} * sizeof(NbEntry));
 }
 CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t fcap) {
@@ -236,6 +237,7 @@ CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t f
     t.fpos = (uint32_t *)p; p += align16(H * 4);
     t.used = (uint32_t *)p; p += align16(cap * 4);
     t.front = (uint64_t *)p; p += align16(cap * 8);
+    t.fslot = (uint32_t *)p; p += align16(cap * 4);
     t.found = (NbEntry *)p;
     t.H = log2 ? (uint32_t)H : 0;
     t.cap = (uint32_t)cap;
@@ -293,6 +295,9 @@ struct Shot {
     uint8_t *dyn;
     uint64_t dyn_cap;
     unsigned long long *prof;  // DecodeParams::phase_cycles (nullable)
+    // lane 0 of every warp sub-allocates small blocks from a private chunk (one global atomic per chunk)
+    uint64_t chunk_off;
+    uint32_t chunk_left;
 
     CB_HD uint32_t *lidx_huge() const { return fillp; }  // free between the member fill and the path phase
     CB_HD uint32_t event_node(uint32_t i) const { return 2 * evdet[i >> 1] + (i & 1); }
@@ -315,6 +320,24 @@ struct Shot {
             return nullptr;
         }
         return dyn + off;
+    }
+    // Small allocation by lane 0 of a warp; amortises the bump-pointer atomic over a 4 KB chunk.
+    CB_HD uint8_t *alloc_small(uint64_t bytes) {
+        bytes = align16(bytes);
+#ifdef CB_NO_CHUNK
+        return alloc(bytes);
+#endif
+        if (bytes > 1024) return alloc(bytes);
+        if (bytes > chunk_left) {
+            uint8_t *c = alloc(4096);
+            if (!c) return nullptr;
+            chunk_off = (uint64_t)(c - dyn);
+            chunk_left = 4096;
+        }
+        uint8_t *r = dyn + chunk_off;
+        chunk_off += bytes;
+        chunk_left -= (uint32_t)bytes;
+        return r;
     }
 };
 
@@ -351,6 +374,8 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.dyn = q;
     s.dyn_cap = align16(p.cfg.dyn_bytes);
     s.prof = p.phase_cycles;
+    s.chunk_off = 0;
+    s.chunk_left = 0;
     s.M = 0;
     // shared memory
     s.nwords = (p.T.num_dets + 31) / 32;
@@ -516,6 +541,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     uint32_t *const fpos = t.fpos;
     uint32_t *const used = t.used;
     uint64_t *const front = t.front;
+    uint32_t *const fslot = t.fslot;
     NbEntry *const found = t.found;
     const uint32_t H = t.H, hmask = t.H - 1, cap = t.cap, fcap = t.fcap;
     const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
@@ -533,6 +559,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
         fpos[k] = 0;
         used[0] = k;
         front[0] = src;
+        fslot[0] = k;
     }
     g.wsync();
     uint32_t nfound = 0;
@@ -541,24 +568,29 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     while (nfront) {
         // pop the closest open node
         uint64_t best = ~uint64_t{0};
+        uint32_t best_q = 0;
         for (uint32_t q = lane; q < nfront; q += lanes) {
             uint64_t cand = front[q];
-            best = cand < best ? cand : best;
+            if (cand < best) {
+                best = cand;
+                best_q = q;
+            }
         }
+        const uint64_t mine = best;
         best = g.min64(best);
         const int64_t d = (int64_t)(best >> 24);
         const uint32_t u = (uint32_t)(best & 0xFFFFFF);
         if (limit >= 0 && (inclusive ? d > limit : d >= limit)) break;
-        uint32_t slot = ht_hash(u, H);
-        while (key[slot] != u) slot = (slot + 1) & hmask;
-        const uint32_t q = fpos[slot];
+        // the lane that held the minimum knows its frontier position (keys are unique: one entry per node)
+        const uint32_t owner = ctz32(g.ballot(mine == best));
+        const uint32_t q = g.shfl32(best_q, (int)owner);
+        const uint32_t slot = fslot[q];
         g.wsync();
         if (lane == 0) {
-            uint64_t last = front[nfront - 1];
-            front[q] = last;
-            uint32_t ls = ht_hash((uint32_t)(last & 0xFFFFFF), H);
-            while (key[ls] != (uint32_t)(last & 0xFFFFFF)) ls = (ls + 1) & hmask;
-            fpos[ls] = q;
+            const uint32_t last_slot = fslot[nfront - 1];
+            front[q] = front[nfront - 1];
+            fslot[q] = last_slot;
+            fpos[last_slot] = q;
             fpos[slot] = FRONT_CLOSED;
         }
         nfront--;
@@ -634,6 +666,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
                 uint32_t idx = popc32(fresh & lane_lt);
                 used[nused + idx] = my_slot;
                 front[nfront + idx] = ((uint64_t)nd << 24) | my_node;
+                fslot[nfront + idx] = my_slot;
                 fpos[my_slot] = nfront + idx;
             }
             const uint32_t c = popc32(fresh);
@@ -679,7 +712,7 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
     }
     uint64_t off = 0;
     if (g.lane == 0) {
-        uint8_t *dst = s.alloc(uint64_t{nfound} * sizeof(NbEntry) + 16);
+        uint8_t *dst = s.alloc_small(uint64_t{nfound} * sizeof(NbEntry) + 16);
         off = dst ? (uint64_t)(dst - s.dyn) + 1 : 0;
     }
     off = g.shfl64(off, 0);
@@ -1450,6 +1483,7 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
 template <class G>
 CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     const uint32_t M = s.M;
+    s.chunk_left = 0;  // the dynamic region was reset for this shot
     for (uint32_t i = g.tid; i < M; i += g.n) {
         s.partner[i] = -1;
         s.solved[i] = 0;
@@ -1644,7 +1678,7 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
         if (pass == 0 && ok) {
             uint64_t off = 0;
             if (g.lane == 0) {
-                uint8_t *mem = s.alloc(uint64_t{len} * 4);
+                uint8_t *mem = s.alloc_small(uint64_t{len} * 4);
                 off = mem ? (uint64_t)(mem - s.dyn) + 1 : 0;
             }
             off = g.shfl64(off, 0);

@@ -18,7 +18,8 @@ print('%s: compile %.2fs sample %.2fs D=%d table_bytes=%d' % (name, t1 - t0, t2 
 ref = None
 def tune(spec):
     parts = str(spec).split(':')
-    dec.set_tuning(group_threads=int(parts[0]), groups_per_sm=int(parts[1]) if len(parts) > 1 else 0)
+    dec.set_tuning(group_threads=int(parts[0]), groups_per_sm=int(parts[1]) if len(parts) > 1 else 0,
+                   ht_log2=int(parts[2]) if len(parts) > 2 else 0)
     return int(parts[0])
 for gspec in groups:
     g = tune(gspec)
