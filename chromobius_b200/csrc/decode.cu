@@ -221,18 +221,21 @@ struct cb200_decoder {
     TablesView dview{};
     uint64_t table_bytes = 0;
     // per-call buffers (grow only)
-    DeviceBuf<uint8_t> d_dets, d_obs_bytes, d_arena;
+    DeviceBuf<uint8_t> d_dets, d_obs_bytes;
+    struct ArenaState {
+        DeviceBuf<uint8_t> buf;
+        ScratchConfig cfg{};
+        uint32_t group = 0, groups = 0;
+        uint64_t stride = 0;
+    } arenas[4];  // one cached arena per escalation level, so retry passes do not evict the main layout
     DeviceBuf<uint64_t> d_obs64;
     DeviceBuf<int64_t> d_wint, d_wint_out, d_edges;
     DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list;
     DeviceBuf<unsigned long long> d_phase;
     bool profile_phases = false;
-    unsigned long long phase_cycles[16] = {};
+    unsigned long long phase_cycles[24] = {};
     DeviceBuf<float> d_wfloat;
     // arena layout currently initialised on the device
-    ScratchConfig arena_cfg{};
-    uint32_t arena_group = 0, arena_groups = 0;
-    uint64_t arena_stride = 0;
     // tuning
     uint32_t tune_group = 0, tune_ht_log2 = 0;
 };
@@ -370,7 +373,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     uint32_t full = 4;
     while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
     uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 8;
-    uint32_t gl = std::min<uint32_t>(full, 13 + 3 * escalation);
+    uint32_t gl = std::min<uint32_t>(full, 14 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
     pl.cfg.sh_found = 16;
     pl.cfg.ht_log2 = gl;
@@ -401,28 +404,28 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     return pl;
 }
 
-void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &launches) {
+void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &launches, uint32_t level) {
+    cb200_decoder::ArenaState &a = d->arenas[level];
     uint32_t nwarps = pl.group == 32 ? 1 : pl.group / 32;
     uint64_t stride = arena_bytes_per_group(pl.cfg, d->dview.num_nodes, nwarps);
-    bool same = d->arena_group == pl.group && d->arena_stride == stride && d->arena_groups >= pl.groups &&
-                memcmp(&d->arena_cfg, &pl.cfg, sizeof(ScratchConfig)) == 0;
+    bool same = a.group == pl.group && a.stride == stride && a.groups >= pl.groups && memcmp(&a.cfg, &pl.cfg, sizeof(ScratchConfig)) == 0;
     p.cfg = pl.cfg;
     p.arena_stride = stride;
     if (!same) {
-        d->d_arena.ensure(stride * pl.groups);
-        p.arena = d->d_arena.ptr;
+        a.buf.ensure(stride * pl.groups);
+        p.arena = a.buf.ptr;
         if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
         else if (pl.group == 128) launch_init<128>(p, pl.groups, d->stream);
         else if (pl.group == 256) launch_init<256>(p, pl.groups, d->stream);
         else launch_init<512>(p, pl.groups, d->stream);
         CUDA_CHECK(cudaGetLastError());
         launches++;
-        d->arena_group = pl.group;
-        d->arena_stride = stride;
-        d->arena_groups = pl.groups;
-        d->arena_cfg = pl.cfg;
+        a.group = pl.group;
+        a.stride = stride;
+        a.groups = pl.groups;
+        a.cfg = pl.cfg;
     }
-    p.arena = d->d_arena.ptr;
+    p.arena = a.buf.ptr;
 }
 
 int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
@@ -492,8 +495,8 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     p.rounds_out = d->d_rounds.ptr;
     p.work_counter = d->d_scalars.ptr + 4;
     if (d->profile_phases) {
-        d->d_phase.ensure(16);
-        CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 128, s));
+        d->d_phase.ensure(24);
+        CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 192, s));
         p.phase_cycles = d->d_phase.ptr;
     }
     if (edges_out || num_edge_ints) {
@@ -508,7 +511,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     for (uint32_t esc = 0; esc < 4; esc++) {
         uint64_t items = esc == 0 ? n : retry.size();
         Plan pl = make_plan(d, items, max_count, (double)total_events / (double)n, esc);
-        ensure_arena(d, pl, p, launches);
+        ensure_arena(d, pl, p, launches, esc);
         if (esc == 0) {
             st.group_threads = pl.group;
             st.num_groups = pl.groups;
@@ -583,7 +586,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         CUDA_CHECK(cudaStreamSynchronize(s));
         for (uint32_t r : rounds) st.matcher_rounds += r;
     }
-    if (d->profile_phases) CUDA_CHECK(cudaMemcpyAsync(d->phase_cycles, d->d_phase.ptr, 128, cudaMemcpyDeviceToHost, s));
+    if (d->profile_phases) CUDA_CHECK(cudaMemcpyAsync(d->phase_cycles, d->d_phase.ptr, 192, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaEventRecord(d->ev[5], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     st.kernel_launches = launches;
@@ -662,7 +665,7 @@ void cb200_free(cb200_decoder *d) {
         cudaStreamSynchronize(d->stream);
     }
     d->d_tables.release();
-    d->d_dets.release(); d->d_obs_bytes.release(); d->d_arena.release(); d->d_obs64.release(); d->d_wint.release();
+    d->d_dets.release(); d->d_obs_bytes.release(); for (auto &a : d->arenas) a.buf.release(); d->d_obs64.release(); d->d_wint.release();
     d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();
     d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release(); d->d_phase.release();
     for (auto &e : d->ev)
@@ -707,9 +710,9 @@ int cb200_set_groups_per_sm(cb200_decoder *d, uint32_t groups_per_sm) {
     return CB200_OK;
 }
 
-int cb200_profile_phases(cb200_decoder *d, int enable, unsigned long long *cycles_out16) {
+int cb200_profile_phases(cb200_decoder *d, int enable, unsigned long long *cycles_out24) {
     if (!d) return CB200_ERR_INVALID_ARGUMENT;
-    if (cycles_out16) memcpy(cycles_out16, d->phase_cycles, sizeof(d->phase_cycles));
+    if (cycles_out24) memcpy(cycles_out24, d->phase_cycles, sizeof(d->phase_cycles));
     d->profile_phases = enable != 0;
     return CB200_OK;
 }

@@ -108,6 +108,7 @@ struct DecodeParams {
     // [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
     // [5] path extraction [6] Euler tours + discharge [7] shots
     // [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events; [12..15] their counts
+    // [16] closed-form component solves [17] per-warp blossoms [18] block-wide blossoms
     unsigned long long *phase_cycles;
 };
 
@@ -133,10 +134,10 @@ CB_HD unsigned long long cb_clock() { return 0; }
 #endif
 
 struct PhaseTimer {
-    unsigned long long t[8];
+    unsigned long long t[12];
     unsigned long long last;
     CB_HD void start() {
-        for (int k = 0; k < 8; k++) t[k] = 0;
+        for (int k = 0; k < 12; k++) t[k] = 0;
         last = cb_clock();
     }
     CB_HD void lap(int phase) {
@@ -768,7 +769,6 @@ struct Blossom {
     bool broken;
     bool par;
     bool wide;         // endpoints stored as u16
-    G g;
 
     static CB_HD uint64_t bytes_needed(int n) {
         int NX = n + n / 2 + 2;
@@ -788,10 +788,15 @@ struct Blossom {
         b += align16(uint64_t(2 * NX + 4) * 2);
         b += align16(uint64_t(n + 1) * AW * 4);
         b += 32;
+        b += align16(sizeof(Blossom));  // the solver state itself lives at the front of its scratch memory
         return b;
     }
-    CB_HD void bind(uint8_t *mem, int n_, const G &g_) {
-        g = g_;
+    // The object is placed in the scratch memory it manages (shared memory for all but giant components): its fields
+    // are read on every step of the sequential bookkeeping, and a copy in a lane's local memory would cost one cache
+    // line per 4 bytes.
+    static CB_HD Blossom *place(uint8_t *mem) { return (Blossom *)mem; }
+    CB_HD void bind(uint8_t *mem, int n_, int lanes) {
+        mem += align16(sizeof(Blossom));
         n = n_;
         NX = n + n / 2 + 2;
         FL = n + 2;
@@ -816,7 +821,7 @@ struct Blossom {
         adjm = (uint32_t *)p; p += align16(uint64_t(n + 1) * AW * 4);
         cmd = (uint32_t *)p;
         broken = false;
-        par = g.lanes > 1 && n >= BLOSSOM_PAR_MIN;
+        par = lanes > 1 && n >= BLOSSOM_PAR_MIN;
         n_x = n;
     }
     CB_HD int64_t &w(int u, int v) { return W[u * (n + 1) + v]; }
@@ -944,7 +949,7 @@ struct Blossom {
     }
 
     // ---- warp dispatch: every lane runs the same helper; results are reduced with warp primitives ----
-    CB_HDN uint64_t dispatch(uint32_t op, uint32_t a0, uint32_t a1, uint32_t a2) {
+    CB_HDN uint64_t dispatch(const G &g, uint32_t op, uint32_t a0, uint32_t a1, uint32_t a2) {
         const int lane = g.lane, lanes = g.lanes;
         uint64_t r = 0;
         switch (op) {
@@ -993,27 +998,27 @@ struct Blossom {
         return r;
     }
     // master side: announce, run together, wait for everyone's writes
-    CB_HD uint64_t call(uint32_t op, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
+    CB_HD uint64_t call(const G &g, uint32_t op, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
         cmd[0] = op;
         cmd[1] = a0;
         cmd[2] = a1;
         cmd[3] = a2;
         g.wsync();
-        uint64_t r = dispatch(op, a0, a1, a2);
+        uint64_t r = dispatch(g, op, a0, a1, a2);
         g.wsync();
         return r;
     }
     // lanes 1..31
-    CB_HDN void worker_loop() {
+    CB_HDN void worker_loop(const G &g) {
         while (true) {
             g.wsync();
             uint32_t op = cmd[0];
             if (op == OP_EXIT) break;
-            dispatch(op, cmd[1], cmd[2], cmd[3]);
+            dispatch(g, op, cmd[1], cmd[2], cmd[3]);
             g.wsync();
         }
     }
-    CB_HD void release_workers() {
+    CB_HD void release_workers(const G &g) {
         if (par) {
             cmd[0] = OP_EXIT;
             g.wsync();
@@ -1024,8 +1029,8 @@ struct Blossom {
     CB_HD void update_slack(int u, int x) {
         if (!slack[x] || edist(u, x) < edist(slack[x], x)) slack[x] = (uint16_t)u;
     }
-    CB_HDN void set_slack(int x) {
-        uint64_t best = par ? call(OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
+    CB_HDN void set_slack(const G &g, int x) {
+        uint64_t best = par ? call(g, OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
         slack[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
     }
     CB_HD void q_put(int v) {
@@ -1127,7 +1132,7 @@ struct Blossom {
         }
         return 0;
     }
-    CB_HDN void add_blossom(int u, int lca, int v) {
+    CB_HDN void add_blossom(const G &g, int u, int lca, int v) {
         int b = n + 1;
         while (b <= n_x && st[b]) ++b;
         if (b > n_x) ++n_x;
@@ -1153,15 +1158,15 @@ struct Blossom {
         }
         fl_len[b] = (uint16_t)len;
         set_st(b, b);
-        if (par) call(OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
+        if (par) call(g, OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
         else k_blossom_clear(0, 1, b, n_x);
         for (int i = 0; i < len; ++i) {
-            if (par) call(OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
+            if (par) call(g, OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
             else k_merge_row(0, 1, b, f[i], n_x);
         }
-        set_slack(b);
+        set_slack(g, b);
     }
-    CB_HDN void expand_blossom(int b) {
+    CB_HDN void expand_blossom(const G &g, int b) {
         uint16_t *f = flower(b);
         int len = fl_len[b];
         for (int i = 0; i < len; ++i) set_st(f[i], f[i]);
@@ -1173,7 +1178,7 @@ struct Blossom {
             S[xs] = 1;
             S[xns] = 0;
             slack[xs] = 0;
-            set_slack(xns);
+            set_slack(g, xns);
             q_push(xns);
         }
         S[xr] = 1;
@@ -1181,12 +1186,12 @@ struct Blossom {
         for (int i = pr + 1; i < len; ++i) {
             int xs = f[i];
             S[xs] = -1;
-            set_slack(xs);
+            set_slack(g, xs);
         }
         st[b] = 0;
     }
     // e = best edge between nodes a (row) and b: endpoints (eu in a, ev in b)
-    CB_HDN bool on_found_edge(int eu, int ev) {
+    CB_HDN bool on_found_edge(const G &g, int eu, int ev) {
         int u = st[eu], v = st[ev];
         if (S[v] == -1) {
             pa[v] = (uint16_t)eu;
@@ -1202,13 +1207,13 @@ struct Blossom {
                 augment(v, u);
                 return true;
             }
-            add_blossom(u, lca, v);
+            add_blossom(g, u, lca, v);
         }
         return false;
     }
-    CB_HDN bool matching() {
+    CB_HDN bool matching(const G &g) {
         const int64_t INF = INT64_MAX / 4;
-        if (par) call(OP_PHASE_INIT, (uint32_t)n_x);
+        if (par) call(g, OP_PHASE_INIT, (uint32_t)n_x);
         else k_phase_init(0, 1, n_x);
         qh = qt = 0;
         for (int x = 1; x <= n_x; ++x)
@@ -1232,7 +1237,7 @@ struct Blossom {
                         bits &= bits - 1;
                         if (st[u] != st[v]) {
                             if (lab[u] + lab[v] - 2 * W[u * (n + 1) + v] == 0) {
-                                if (on_found_edge(u, v)) return true;
+                                if (on_found_edge(g, u, v)) return true;
                             } else {
                                 update_slack(u, st[v]);
                             }
@@ -1241,35 +1246,35 @@ struct Blossom {
                 }
             }
             if (broken) return false;
-            int64_t d = (int64_t)(par ? call(OP_DUAL_MIN, (uint32_t)n_x) : k_dual_min(0, 1, n_x));
+            int64_t d = (int64_t)(par ? call(g, OP_DUAL_MIN, (uint32_t)n_x) : k_dual_min(0, 1, n_x));
             if (d >= INF) return false;
-            if (par) call(OP_LAB_UPDATE, (uint32_t)n_x, (uint32_t)((uint64_t)d & 0xFFFFFFFFu), (uint32_t)((uint64_t)d >> 32));
+            if (par) call(g, OP_LAB_UPDATE, (uint32_t)n_x, (uint32_t)((uint64_t)d & 0xFFFFFFFFu), (uint32_t)((uint64_t)d >> 32));
             else k_lab_update(0, 1, n_x, d);
             qh = qt = 0;
             if (par) {
-                for (int x = (int)call(OP_NEXT_TIGHT, 1, (uint32_t)n_x); x <= n_x; x = (int)call(OP_NEXT_TIGHT, (uint32_t)(x + 1), (uint32_t)n_x))
-                    if (tight_candidate(x) && on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+                for (int x = (int)call(g, OP_NEXT_TIGHT, 1, (uint32_t)n_x); x <= n_x; x = (int)call(g, OP_NEXT_TIGHT, (uint32_t)(x + 1), (uint32_t)n_x))
+                    if (tight_candidate(x) && on_found_edge(g, geu(slack[x], x), gev(slack[x], x))) return true;
             } else {
                 for (int x = 1; x <= n_x; ++x)
                     if (tight_candidate(x))
-                        if (on_found_edge(geu(slack[x], x), gev(slack[x], x))) return true;
+                        if (on_found_edge(g, geu(slack[x], x), gev(slack[x], x))) return true;
             }
             for (int b = n + 1; b <= n_x; ++b)
-                if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(b);
+                if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(g, b);
         }
     }
     // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match[1..n] = partners.
-    CB_HDN int solve() {
+    CB_HDN int solve(const G &g) {
         n_x = n;
         vis_t = 0;
         if (par) {
-            call(OP_INIT);
+            call(g, OP_INIT);
         } else {
             k_init(0, 1);
             k_set_lab(0, 1, k_wmax(0, 1));
         }
         int cnt = 0;
-        while (matching()) ++cnt;
+        while (matching(g)) ++cnt;
         return cnt;
     }
 };
@@ -1426,10 +1431,11 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
     }
     off = g.shfl64(off, 0);
     if (!off) return;
-    Blossom<G> bl;
-    bl.bind((uint8_t *)(uintptr_t)off, (int)n, g);
+    Blossom<G> &bl = *Blossom<G>::place((uint8_t *)(uintptr_t)off);
+    if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
+    g.wsync();
     if (g.lane != 0) {
-        if (bl.par) bl.worker_loop();
+        if (bl.par) bl.worker_loop(g);
         return;
     }
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
@@ -1451,8 +1457,8 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
             bl.w((int)b, (int)a + 1) = big - l[k].d;
         }
     }
-    int pairs = bl.solve();
-    bl.release_workers();
+    int pairs = bl.solve(g);
+    bl.release_workers(g);
     if (s.prof) {
         int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
         cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
@@ -1569,6 +1575,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         for (uint32_t c = g.tid; c < ncomp; c += g.n)
             if (!solve_component_small(s, c)) s.uf[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
+        pt.lap(8);
         const uint32_t nbig = s.hdr->nbig;
         // blossom components that fit a warp's shared-memory table space: one warp each, in parallel
         bool dirtied_shared = false;
@@ -1583,6 +1590,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             dirtied_shared = true;
         }
         g.sync();
+        pt.lap(9);
         // the few components that do not: one after the other on warp 0, in the whole block's table space
         const uint32_t nhuge = s.hdr->nhuge;
         if (nhuge) {
@@ -1599,7 +1607,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
         }
         g.sync();
-        pt.lap(3);
+        pt.lap(10);
         const uint32_t st = s.hdr->status;
         const uint32_t ngrow = s.hdr->ngrow;
         g.sync();  // everyone has read the verdict before the next phase may change it
@@ -1613,13 +1621,44 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Matched pair -> graph edges along the canonical shortest path: among equal-length paths, walking back from the
-// larger event index towards the smaller one always steps to the smallest-id tight predecessor. Stored as the node
+// Matched pair -> graph edges along the canonical shortest path: a direct edge of the pair's distance if there is one,
+// otherwise, among equal-length paths, walking back from the larger event index towards the smaller one always steps
+// to the smallest-id tight predecessor. Stored as the node
 // sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
 template <class G>
 CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_total) {
     const uint32_t src = s.event_node(i), dst = s.event_node(j);
+    // Most matched pairs are graph neighbours: a direct edge of exactly the pair's distance is the path.
+    {
+        const RowRange row = row_of(s.T, src);
+        const AdjEntry *adj = adj_of(s.T);
+        bool direct = false;
+        for (uint32_t base = row.e0; base < row.e1 && !direct; base += g.lanes) {
+            uint32_t e = base + g.lane;
+            bool hit = false;
+            if (e < row.e1) {
+                AdjEntry a = adj[e];
+                hit = a.nbr == dst && a.wt == d_total;
+            }
+            direct = g.ballot(hit) != 0;
+        }
+        if (direct) {
+            uint64_t off = 0;
+            if (g.lane == 0) {
+                uint8_t *mem = s.alloc_small(8);
+                off = mem ? (uint64_t)(mem - s.dyn) + 1 : 0;
+                if (mem) {
+                    ((uint32_t *)mem)[0] = src;
+                    ((uint32_t *)mem)[1] = dst;
+                    s.path_off[i] = (uint32_t)((off - 1) >> 4);
+                    s.path_len[i] = 2;
+                }
+            }
+            g.wsync();
+            return;
+        }
+    }
     int64_t limit = 0;
     uint32_t nfound = 0;
     BallTables *t = nullptr;
@@ -2031,8 +2070,10 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
     if (g.tid == 0) {
         pt.lap(6);
         if (p.phase_cycles) {
+            pt.t[3] = pt.t[8] + pt.t[9] + pt.t[10];
             for (int k = 0; k < 7; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[k], pt.t[k]);
             cb_atomic_add64((uint64_t *)&p.phase_cycles[7], 1);
+            for (int k = 8; k < 11; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[8 + k], pt.t[k]);
         }
         uint32_t st = s.hdr->status;
         p.status_out[shot] = st;

@@ -106,8 +106,9 @@ int cb200_set_groups_per_sm(cb200_decoder *dec, uint32_t groups_per_sm);
  * for later calls and copies out the counters of the most recent profiled call:
  * [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
  * [5] path extraction [6] Euler tours + discharge [7] number of shots
- * [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events, [12..15] how many of each. */
-int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cycles_out16);
+ * [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events, [12..15] how many of each
+ * [16] closed-form component solves [17] per-warp blossoms [18] block-wide blossoms (the three parts of [3]). */
+int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cycles_out24);
 
 /* Sizes of the device-resident tables, for DESIGN.md / bench reporting. */
 uint64_t cb200_table_bytes(const cb200_decoder *dec);

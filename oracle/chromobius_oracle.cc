@@ -1151,9 +1151,16 @@ struct Decoder {
         for (auto v : touched) dist[v] = -1;
     }
 
-    // Canonical shortest path src -> dst: full distances from src (bounded by d(src,dst)), then walk back from dst
-    // always taking the smallest-id tight predecessor. Emits edges in walking order from src to dst.
+    // Canonical shortest path src -> dst. A direct graph edge of length d(src,dst) is taken as it is; otherwise: full
+    // distances from src (bounded by d(src,dst)), then walk back from dst always taking the smallest-id tight
+    // predecessor. Emits edges in walking order from src to dst.
     void canonical_path(node_t src, node_t dst, int64_t d_total, std::vector<int64_t> *out_edges) {
+        for (uint32_t k = t->row_ptr[src]; k < t->row_ptr[src + 1]; k++)
+            if (t->nbr[k] == dst && t->wt[k] == d_total) {
+                out_edges->push_back(src);
+                out_edges->push_back(dst);
+                return;
+            }
         ReusableHeap &pq = heap_buf;
         pq.clear();
         touched.clear();
