@@ -109,6 +109,7 @@ struct DecodeParams {
     // [5] path extraction [6] Euler tours + discharge [7] shots
     // [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events; [12..15] their counts
     // [16] closed-form component solves [17] per-warp blossoms [18] block-wide blossoms
+    // [19] ball pops [20] cycles inside ball_grow [21] balls [22] nodes touched by balls
     unsigned long long *phase_cycles;
 };
 
@@ -566,7 +567,17 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     uint32_t nfound = 0;
     int64_t limit = radius;
     int result = BALL_OK;
+    // Pruning (changes no result). Nearest-event search (radius < 0, need_more_than == 0): `cand` is the smallest
+    // tentative distance of an event seen so far; nothing beyond it can be settled before the search stops, so nodes
+    // beyond it are not inserted and a settled node whose every edge leads beyond it is not relaxed at all.
+    // Radius searches prune against the radius in the same way.
+    const int64_t min_wt = s.T.min_wt;
+    const bool nearest_only = radius < 0 && need_more_than == 0 && collect_events;
+    int64_t cand = INT64_MAX / 4;
+    const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
+    uint32_t prof_pops = 0;
     while (nfront) {
+        prof_pops++;
         // pop the closest open node
         uint64_t best = ~uint64_t{0};
         uint32_t best_q = 0;
@@ -582,6 +593,42 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
         const int64_t d = (int64_t)(best >> 24);
         const uint32_t u = (uint32_t)(best & 0xFFFFFF);
         if (limit >= 0 && (inclusive ? d > limit : d >= limit)) break;
+        if (nearest_only && d + min_wt > cand) {
+            // No relaxation can reach cand any more, so every tentative distance up to cand is final: the answer is the
+            // open event at distance cand with the smallest node id -- exactly the node the settling order would reach.
+            uint64_t hit = ~uint64_t{0};
+            for (uint32_t q = lane; q < nfront; q += lanes) {
+                const uint64_t cnd = front[q];
+                const uint32_t node = (uint32_t)(cnd & 0xFFFFFF);
+                const uint32_t det = node >> 1;
+                if ((int64_t)(cnd >> 24) == cand && node != src && ((words[det >> 5] >> (det & 31)) & 1) && cnd < hit) hit = cnd;
+            }
+            hit = g.min64(hit);
+            const uint32_t node = (uint32_t)(hit & 0xFFFFFF);
+            const uint32_t det = node >> 1;
+            if (lane == 0) {
+                const uint32_t w = words[det >> 5];
+                found[0].ev = 2 * (word_rank[det >> 5] + popc32(w & ((1u << (det & 31)) - 1))) + (node & 1);
+                found[0].pad = 0;
+                found[0].d = cand;
+            }
+            nfound = 1;
+            limit = cand;
+            break;
+        }
+        // Start fetching the node's adjacency row now; the frontier bookkeeping below hides part of the latency.
+        uint32_t e0, e1;
+        if (ell_shift) {
+            e0 = u << ell_shift;
+            e1 = e0 + (1u << ell_shift);
+        } else {
+            e0 = row_ptr[u];
+            e1 = row_ptr[u + 1];
+        }
+        AdjEntry first_seg;
+        first_seg.nbr = NO_INDEX;
+        first_seg.wt = 0;
+        if (e0 + lane < e1) first_seg = adj[e0 + lane];
         // the lane that held the minimum knows its frontier position (keys are unique: one entry per node)
         const uint32_t owner = ctz32(g.ballot(mine == best));
         const uint32_t q = g.shfl32(best_q, (int)owner);
@@ -617,29 +664,27 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
                 }
             }
         }
-        uint32_t e0, e1;
-        if (ell_shift) {
-            e0 = u << ell_shift;
-            e1 = e0 + (1u << ell_shift);
-        } else {
-            e0 = row_ptr[u];
-            e1 = row_ptr[u + 1];
-        }
+        if (nearest_only ? d + min_wt > cand : (limit >= 0 && (inclusive ? d + min_wt > limit : d + min_wt >= limit))) continue;
         if (nused + (e1 - e0) > cap) {
             result = BALL_OVERFLOW;
             break;
         }
+        int64_t step_cand = cand;
         for (uint32_t base = e0; base < e1; base += lanes) {
             const uint32_t e = base + lane;
             bool is_new = false, too_far = false;
             uint32_t my_slot = 0, my_node = 0;
             int64_t nd = 0;
             if (e < e1) {
-                AdjEntry a = adj[e];
+                AdjEntry a = base == e0 ? first_seg : adj[e];
                 nd = d + a.wt;
                 my_node = a.nbr;
-                if (a.nbr != NO_INDEX && !(limit >= 0 && (inclusive ? nd > limit : nd >= limit))) {
+                if (a.nbr != NO_INDEX && !(limit >= 0 && (inclusive ? nd > limit : nd >= limit)) && nd <= cand) {
                     too_far = nd >= (int64_t{1} << 39);  // frontier keys hold 40 distance bits
+                    if (nearest_only && a.nbr != src) {
+                        const uint32_t det = a.nbr >> 1;
+                        if (((words[det >> 5] >> (det & 31)) & 1) && nd < step_cand) step_cand = nd;
+                    }
                     uint32_t k = ht_hash(a.nbr, H);
                     while (true) {
                         uint32_t old = cb_atomic_cas(&key[k], HT_EMPTY, a.nbr);
@@ -676,10 +721,17 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
             g.wsync();
             if (g.ballot(too_far)) result = BALL_OVERFLOW;
         }
+        if (nearest_only) cand = (int64_t)g.min64((uint64_t)step_cand);
         if (result != BALL_OK) break;
     }
     t.nused = nused;
     t.nfront = nfront;
+    if (s.prof && lane == 0) {
+        cb_atomic_add64((uint64_t *)&s.prof[19], prof_pops);
+        cb_atomic_add64((uint64_t *)&s.prof[20], cb_clock() - prof_t0);
+        cb_atomic_add64((uint64_t *)&s.prof[21], 1);
+        cb_atomic_add64((uint64_t *)&s.prof[22], nused);
+    }
     if (result == BALL_OK && limit < 0) result = BALL_EXHAUSTED;
     *limit_out = limit;
     *nfound_out = nfound;

@@ -909,6 +909,14 @@ HostTables compile_tables(const FlatDem &dem) {
                     t.ell_adj[((size_t)u << sh) + (k - t.row_ptr[u])] = t.adj[k];
         }
     }
+    {
+        int64_t mw = 0;
+        for (const auto &a : t.adj) {
+            if (a.wt <= 0) fail("The matcher graph has an edge of non-positive weight; such detector error models are not supported.");
+            if (mw == 0 || a.wt < mw) mw = a.wt;
+        }
+        t.min_wt = (int32_t)mw;
+    }
     t.det_info.assign(t.num_dets, 0);
     t.rep_obs.assign(t.num_dets, 0);
     t.ingest_mask.assign((t.num_dets + 7) / 8, 0);
@@ -933,6 +941,7 @@ TablesView HostTables::view() const {
     v.adj = adj.data();
     v.ell_adj = ell_adj.data();
     v.ell_shift = ell_shift;
+    v.min_wt = min_wt;
     v.adj_drag = adj_drag.data();
     v.det_info = det_info.data();
     v.rep_obs = rep_obs.data();

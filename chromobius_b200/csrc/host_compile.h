@@ -73,6 +73,7 @@ struct HostTables {
     std::vector<AdjEntry> adj;
     std::vector<AdjEntry> ell_adj;   // fixed-stride copy of adj (1 << ell_shift entries per node), see TablesView
     uint32_t ell_shift = 0;
+    int32_t min_wt = 0;              // smallest edge weight (0 when the graph has no edges)
     std::vector<uint32_t> adj_drag;
     std::vector<uint8_t> det_info;
     std::vector<uint64_t> rep_obs;

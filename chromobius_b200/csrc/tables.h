@@ -47,6 +47,7 @@ struct TablesView {
     const AdjEntry *adj;      // [row_ptr[num_nodes]] sorted by nbr within a row
     const AdjEntry *ell_adj;  // [num_nodes << ell_shift] the same rows at a fixed stride, padded with nbr == NO_INDEX
     uint32_t ell_shift;       // 0: no fixed-stride copy (maximum degree above 32)
+    int32_t min_wt;           // smallest edge weight of the graph (> 0)
     const uint32_t *adj_drag; // [row_ptr[num_nodes]] DragEntry index of the detector pair of this half-edge
     const uint8_t *det_info;  // [num_dets]
     const uint64_t *rep_obs;  // [num_dets] rgb_reps[d].obs_flip
