@@ -275,7 +275,7 @@ class CompiledDecoder:
         self._L.cb200_profile_phases(self._h, 1 if enable else 0, buf)
         names = ['ingest', 'explore_first', 'components', 'solve', 'explore_regrow', 'paths', 'lift', 'shots',
                  'blossom_le8', 'blossom_le16', 'blossom_le32', 'blossom_gt32', 'n_le8', 'n_le16', 'n_le32', 'n_gt32',
-                 'solve_closed_form', 'solve_warp_blossoms', 'solve_block_blossoms', 'ball_pops', 'ball_cycles', 'balls', 'ball_nodes', 'spare']
+                 'solve_closed_form', 'solve_warp_blossoms', 'solve_block_blossoms', 'ball_pops', 'ball_cycles', 'balls', 'ball_nodes', 'near_queries']
         return dict(zip(names, [int(x) for x in buf]))
 
     def describe(self):

@@ -253,6 +253,7 @@ void upload_tables(cb200_decoder *d) {
         return off;
     };
     // hot first: the window covers a prefix if the set-aside is smaller than the tables
+    size_t o_near = reserve(h.near.size() * sizeof(NearEntry));
     size_t o_ell = reserve(h.ell_adj.size() * sizeof(AdjEntry));
     size_t o_row = reserve(h.row_ptr.size() * 4);
     size_t o_adj = reserve(h.adj.size() * sizeof(AdjEntry));
@@ -267,6 +268,7 @@ void upload_tables(cb200_decoder *d) {
     auto put = [&](size_t off, const void *src, size_t bytes) {
         if (bytes) CUDA_CHECK(cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice));
     };
+    put(o_near, h.near.data(), h.near.size() * sizeof(NearEntry));
     put(o_ell, h.ell_adj.data(), h.ell_adj.size() * sizeof(AdjEntry));
     put(o_row, h.row_ptr.data(), h.row_ptr.size() * 4);
     put(o_adj, h.adj.data(), h.adj.size() * sizeof(AdjEntry));
@@ -278,6 +280,7 @@ void upload_tables(cb200_decoder *d) {
     put(o_drag, h.drag.data(), h.drag.size() * sizeof(DragEntry));
     d->table_bytes = total;
     TablesView v = h.view();
+    v.near = h.near_stride ? (const NearEntry *)(base + o_near) : nullptr;
     v.ell_adj = (const AdjEntry *)(base + o_ell);
     v.row_ptr = (const uint32_t *)(base + o_row);
     v.adj = (const AdjEntry *)(base + o_adj);

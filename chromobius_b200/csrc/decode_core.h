@@ -109,7 +109,8 @@ struct DecodeParams {
     // [5] path extraction [6] Euler tours + discharge [7] shots
     // [8..11] blossom cycles for components of <= 8, <= 16, <= 32, > 32 events; [12..15] their counts
     // [16] closed-form component solves [17] per-warp blossoms [18] block-wide blossoms
-    // [19] ball pops [20] cycles inside ball_grow [21] balls [22] nodes touched by balls
+    // [19] ball pops [20] cycles inside ball_grow [21] balls [22] nodes touched by balls [23] ball queries answered by
+    // the near table
     unsigned long long *phase_cycles;
 };
 
@@ -740,9 +741,114 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
 
 CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry *)(s.dyn + ((uint64_t)s.nb_off[i] << 4)); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Near-table ball queries. The row of a node lists its closest nodes in the order a ball would settle them
+// (tables.h), so a ball query is a scan of the row against the shot's event bits. Both routines return false when the
+// row ends before the query is decided; the caller then runs the Dijkstra search, which gives the same answer.
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD const NearEntry *near_at(const TablesView &T, uint32_t node, uint32_t p) {
+    return T.near + ((uint64_t)(p >> 5) * T.num_nodes + node) * 32 + (p & 31);
+}
+CB_HD uint32_t nth_set_bit(uint32_t mask, uint32_t n) {  // position of the n-th (0-based) set bit
+    while (n--) mask &= mask - 1;
+    return ctz32(mask);
+}
+
+// Same contract as ball_grow(..., collect_events = true, inclusive = false) followed by the copy into the neighbour
+// list of event i: on success nb_off / nb_cnt / R / regrown of event i are written.
+template <class G>
+CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
+    const uint32_t stride = s.T.near_stride;
+    if (!stride) return false;
+    const uint32_t src = s.event_node(i);
+    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane_lt = (1u << lane) - 1;
+    const uint32_t *const words = s.words;
+    const uint32_t *const word_rank = s.word_rank;
+    // pass 1: how far the row has to be read, and how many events that reports
+    uint32_t nfound = 0, end_pos = 0;  // entries [0, end_pos) take part
+    int64_t limit = radius;
+    bool decided = false;
+    for (uint32_t pos = 0; pos < stride && !decided; pos += lanes) {
+        const NearEntry e = *near_at(s.T, src, pos + lane);
+        const bool pad = e.dist_flag == NEAR_PAD;
+        const int64_t d = (int64_t)(e.dist_flag & 0x7FFFFFFFu);
+        const uint32_t det = (e.node_pred & 0xFFFFFFu) >> 1;
+        const bool in_range = !pad && (radius < 0 || d < radius);
+        const bool is_ev = in_range && ((words[det >> 5] >> (det & 31)) & 1);
+        const uint32_t evs = g.ballot(is_ev);
+        const uint32_t outs = g.ballot(!in_range);
+        if (radius < 0) {
+            const uint32_t usable = outs ? evs & ((1u << ctz32(outs)) - 1) : evs;  // events before the first pad entry
+            if (nfound + popc32(usable) > need_more_than) {
+                const uint32_t l = nth_set_bit(usable, need_more_than - nfound);
+                limit = (int64_t)(g.shfl32(e.dist_flag, (int)l) & 0x7FFFFFFFu);
+                nfound = need_more_than + 1;
+                end_pos = pos + l + 1;
+                decided = true;
+            } else if (outs) {
+                return false;  // the row ends (graph exhausted): the search reports that
+            } else {
+                nfound += popc32(evs);
+            }
+        } else {
+            if (outs) {
+                const uint32_t l = ctz32(outs);  // sorted by distance: everything from here on is outside the radius
+                nfound += popc32(evs & ((1u << l) - 1));
+                end_pos = pos + l;
+                decided = true;
+            } else {
+                nfound += popc32(evs);
+            }
+        }
+    }
+    if (!decided) return false;
+    uint64_t off = 0;
+    if (lane == 0) {
+        uint8_t *dst = s.alloc_small(uint64_t{nfound} * sizeof(NbEntry) + 16);
+        off = dst ? (uint64_t)(dst - s.dyn) + 1 : 0;
+    }
+    off = g.shfl64(off, 0);
+    if (!off) return true;  // alloc flagged the overflow
+    NbEntry *dst = (NbEntry *)(s.dyn + (off - 1));
+    uint32_t run = 0;
+    for (uint32_t pos = 0; pos < end_pos; pos += lanes) {
+        const uint32_t p = pos + lane;
+        bool is_ev = false;
+        NearEntry e;
+        e.node_pred = 0;
+        e.dist_flag = 0;
+        if (p < end_pos) {
+            e = *near_at(s.T, src, p);
+            const uint32_t det = (e.node_pred & 0xFFFFFFu) >> 1;
+            is_ev = (words[det >> 5] >> (det & 31)) & 1;
+        }
+        const uint32_t evs = g.ballot(is_ev);
+        if (is_ev) {
+            const uint32_t node = e.node_pred & 0xFFFFFFu, det = node >> 1;
+            NbEntry out;
+            out.ev = 2 * (word_rank[det >> 5] + popc32(words[det >> 5] & ((1u << (det & 31)) - 1))) + (node & 1);
+            out.pad = 0;
+            out.d = (int64_t)(e.dist_flag & 0x7FFFFFFFu);
+            dst[run + popc32(evs & lane_lt)] = out;
+        }
+        run += popc32(evs);
+    }
+    if (lane == 0) {
+        s.regrown[i] = 1;
+        s.nb_off[i] = (uint32_t)((off - 1) >> 4);
+        s.nb_cnt[i] = nfound;
+        s.R[i] = limit;
+        if (s.prof) cb_atomic_add64((uint64_t *)&s.prof[23], 1);
+    }
+    g.wsync();
+    return true;
+}
+
 // Grows the ball of event i (one warp). Writes nb_off/nb_cnt/R of event i and flags it as regrown.
 template <class G>
 CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint32_t need_more_than) {
+    if (explore_event_near(s, g, i, radius, need_more_than)) return;
     const uint32_t src = s.event_node(i);
     int64_t limit = 0;
     uint32_t nfound = 0;
@@ -1678,9 +1784,54 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 // to the smallest-id tight predecessor. Stored as the node
 // sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
+// Path of a matched pair from the near table of `src`: find `dst` in the row, then follow the stored canonical
+// predecessors. Returns false when dst is not in the row (the caller searches instead).
+template <class G>
+CB_HDN bool extract_path_near(Shot &s, const G &g, uint32_t i, uint32_t src, uint32_t dst, int64_t d_total) {
+    const uint32_t stride = s.T.near_stride;
+    if (!stride) return false;
+    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    uint32_t at = NO_INDEX;
+    for (uint32_t pos = 0; pos < stride; pos += lanes) {
+        const NearEntry e = *near_at(s.T, src, pos + lane);
+        const bool pad = e.dist_flag == NEAR_PAD;
+        const int64_t d = (int64_t)(e.dist_flag & 0x7FFFFFFFu);
+        const uint32_t hits = g.ballot(!pad && (e.node_pred & 0xFFFFFFu) == dst && d == d_total);
+        if (hits) {
+            at = pos + ctz32(hits);
+            break;
+        }
+        if (g.ballot(pad || d > d_total)) return false;
+    }
+    if (at == NO_INDEX) return false;
+    if (lane == 0) {
+        const NearEntry last = *near_at(s.T, src, at);
+        uint32_t len = 2;
+        if (!(last.dist_flag & 0x80000000u))
+            for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; q = near_at(s.T, src, q)->node_pred >> 24) len++;
+        uint32_t *out = (uint32_t *)s.alloc_small(uint64_t{len} * 4);
+        if (out) {
+            out[0] = src;
+            out[len - 1] = dst;
+            uint32_t k = len - 2;
+            if (len > 2)
+                for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; k--) {
+                    const uint32_t np = near_at(s.T, src, q)->node_pred;
+                    out[k] = np & 0xFFFFFFu;
+                    q = np >> 24;
+                }
+            s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
+            s.path_len[i] = len;
+        }
+    }
+    g.wsync();
+    return true;
+}
+
 template <class G>
 CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_total) {
     const uint32_t src = s.event_node(i), dst = s.event_node(j);
+    if (extract_path_near(s, g, i, src, dst, d_total)) return;
     // Most matched pairs are graph neighbours: a direct edge of exactly the pair's distance is the path.
     {
         const RowRange row = row_of(s.T, src);

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 namespace cb200 {
@@ -855,7 +856,88 @@ const char *charge_name(unsigned c) {
 
 }  // namespace
 
-HostTables compile_tables(const FlatDem &dem) {
+// Neighbourhood table (tables.h): one truncated Dijkstra per node, popped in (distance, node id) order -- with positive
+// weights every node at distance d is open before the first of them is popped, so the pop order is the sorted order
+// and the first `stride` pops are exactly the `stride` closest nodes. Independent per node: spread over host threads.
+void build_near_table(HostTables &t, uint32_t stride) {
+    t.near.clear();
+    t.near_stride = 0;
+    const uint32_t n = t.num_dets * 2;
+    if (stride == 0 || n == 0 || t.adj.empty()) return;
+    stride = std::min<uint32_t>((stride + 31) / 32 * 32, NEAR_MAX_STRIDE);
+    t.near.assign((size_t)stride * n, NearEntry{NEAR_PAD, NEAR_PAD});
+    t.near_stride = stride;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    nthreads = std::min<unsigned>(nthreads, 32);
+    if (n < 4096) nthreads = 1;
+    const uint32_t *row_ptr = t.row_ptr.data();
+    const AdjEntry *adj = t.adj.data();
+    NearEntry *near = t.near.data();
+    auto worker = [=](unsigned tid) {
+        constexpr uint16_t OPEN = 0xFFFF, IS_SRC = 0xFFFE;
+        std::vector<int64_t> dist(n, -1);
+        std::vector<uint16_t> pos(n, OPEN);
+        std::vector<uint32_t> touched;
+        std::vector<std::pair<int64_t, uint32_t>> heap;
+        auto cmp = [](const std::pair<int64_t, uint32_t> &a, const std::pair<int64_t, uint32_t> &b) { return a > b; };
+        for (uint32_t u = tid; u < n; u += nthreads) {
+            touched.clear();
+            heap.clear();
+            dist[u] = 0;
+            pos[u] = IS_SRC;
+            touched.push_back(u);
+            auto relax = [&](uint32_t v, int64_t dv) {
+                for (uint32_t e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
+                    const uint32_t w = adj[e].nbr;
+                    const int64_t nd = dv + adj[e].wt;
+                    if (dist[w] < 0) touched.push_back(w);
+                    else if (nd >= dist[w]) continue;
+                    dist[w] = nd;
+                    heap.emplace_back(nd, w);
+                    std::push_heap(heap.begin(), heap.end(), cmp);
+                }
+            };
+            relax(u, 0);
+            uint32_t count = 0;
+            while (!heap.empty() && count < stride) {
+                std::pop_heap(heap.begin(), heap.end(), cmp);
+                const int64_t d = heap.back().first;
+                const uint32_t v = heap.back().second;
+                heap.pop_back();
+                if (pos[v] != OPEN || d != dist[v]) continue;
+                if (d >= 0x7FFFFFFF) break;
+                uint32_t pred = NO_INDEX;
+                bool direct = false;
+                for (uint32_t e = row_ptr[v]; e < row_ptr[v + 1]; e++) {
+                    const uint32_t w = adj[e].nbr;
+                    if (pos[w] == OPEN || dist[w] + adj[e].wt != d) continue;
+                    if (w == u) direct = true;
+                    if (pred == NO_INDEX) pred = pos[w] == IS_SRC ? NEAR_PRED_SRC : pos[w];
+                }
+                NearEntry &out = near[((size_t)(count >> 5) * n + u) * 32 + (count & 31)];
+                out.node_pred = v | (pred << 24);
+                out.dist_flag = (uint32_t)d | (direct ? 0x80000000u : 0u);
+                pos[v] = (uint16_t)count;
+                count++;
+                if (count < stride) relax(v, d);
+            }
+            for (uint32_t w : touched) {
+                dist[w] = -1;
+                pos[w] = OPEN;
+            }
+        }
+    };
+    if (nthreads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned k = 0; k < nthreads; k++) pool.emplace_back(worker, k);
+        for (auto &th : pool) th.join();
+    }
+}
+
+HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
     HostTables t;
     if (dem.num_detectors > 0x7FFFFFFEull) fail("The detector error model is too large.");
     if (dem.num_detectors * 2 > (1ull << 24))
@@ -928,6 +1010,14 @@ HostTables compile_tables(const FlatDem &dem) {
         t.rep_obs[d] = r.obs_flip;
         if (!t.ignored[d]) t.ingest_mask[d >> 3] |= (uint8_t)(1u << (d & 7));
     }
+    if (near_stride == NEAR_STRIDE_AUTO) {
+        // as many entries per node as a 64 MB table holds: the hot part (first chunk of every row) stays far below that
+        const uint64_t budget = 64ull << 20;
+        const uint64_t nodes = std::max<uint64_t>(uint64_t{t.num_dets} * 2, 1);
+        near_stride = (uint32_t)std::min<uint64_t>(budget / (nodes * sizeof(NearEntry)) / 32 * 32, NEAR_MAX_STRIDE);
+        if (const char *env = std::getenv("CB200_NEAR_STRIDE")) near_stride = (uint32_t)std::strtoul(env, nullptr, 10);
+    }
+    build_near_table(t, near_stride);
     return t;
 }
 
@@ -948,6 +1038,8 @@ TablesView HostTables::view() const {
     v.self_drag = self_drag.data();
     v.ingest_mask = ingest_mask.data();
     v.drag = drag.data();
+    v.near = near_stride ? near.data() : nullptr;
+    v.near_stride = near_stride;
     return v;
 }
 

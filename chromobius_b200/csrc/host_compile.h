@@ -81,6 +81,8 @@ struct HostTables {
     std::vector<uint8_t> ingest_mask;
     std::vector<DragEntry> drag;
     std::vector<uint32_t> drag_pair;  // (n1, n2) per DragEntry, n1 <= n2
+    std::vector<NearEntry> near;      // neighbourhood table, see tables.h
+    uint32_t near_stride = 0;
 
     TablesView view() const;
 
@@ -91,7 +93,12 @@ struct HostTables {
 };
 
 // Throws std::invalid_argument with the reference's messages where tests pin them.
-HostTables compile_tables(const FlatDem &dem);
+// near_stride: entries per node of the neighbourhood table (multiple of 32, <= NEAR_MAX_STRIDE); 0 = no table;
+// NEAR_STRIDE_AUTO sizes it from a byte budget (environment CB200_NEAR_STRIDE overrides).
+constexpr uint32_t NEAR_STRIDE_AUTO = 0xFFFFFFFFu;
+HostTables compile_tables(const FlatDem &dem, uint32_t near_stride = NEAR_STRIDE_AUTO);
+// (Re)builds t.near for the given stride from t.row_ptr / t.adj (multi-threaded).
+void build_near_table(HostTables &t, uint32_t near_stride);
 
 }  // namespace cb200
 

@@ -37,6 +37,25 @@ struct AdjEntry {
     int32_t wt;
 };
 
+// Neighbourhood table ("near table"): for every Moebius node the NEAR_K closest other nodes in (distance, node id)
+// order -- exactly the order in which a Dijkstra ball around the node settles them -- with the exact distance and the
+// canonical shortest-path predecessor. A ball query that stays inside the table is one or two coalesced row reads and a
+// ballot against the shot's event bits instead of a Dijkstra search; queries that leave it fall back to the search.
+//   node_pred : bits 0-23 node id, bits 24-31 position (within the same row) of the canonical predecessor on the
+//               shortest path from the row's node, NEAR_PRED_SRC when the predecessor is the row's node itself.
+//               Canonical = the smallest-id neighbour w of the entry with dist(w) + wt(w, entry) == dist(entry).
+//   dist_flag : bits 0-30 exact distance, bit 31 set when the row's node and the entry are joined by a direct edge of
+//               exactly that weight. Rows shorter than the stride are padded with dist_flag == NEAR_PAD.
+// Layout: chunk-major, 32 entries per chunk: entry p of node u sits at ((p >> 5) * num_nodes + u) * 32 + (p & 31), so
+// the first chunks of all rows (the hot part) are contiguous.
+struct NearEntry {
+    uint32_t node_pred;
+    uint32_t dist_flag;
+};
+constexpr uint32_t NEAR_PAD = 0xFFFFFFFFu;
+constexpr uint32_t NEAR_PRED_SRC = 0xFFu;
+constexpr uint32_t NEAR_MAX_STRIDE = 224;  // predecessor positions are 8 bits, 0xFF is reserved
+
 // Views used by the per-shot code (host build and device build alike).
 struct TablesView {
     uint32_t num_dets;
@@ -54,6 +73,8 @@ struct TablesView {
     const uint32_t *self_drag;// [num_dets] DragEntry index of {d, d} or NO_INDEX
     const uint8_t *ingest_mask; // [num_det_bytes] 1-bits for detectors that exist and are not ignored
     const DragEntry *drag;    // [num_drag]
+    const NearEntry *near;    // [near_stride * num_nodes] chunk-major (nullable)
+    uint32_t near_stride;     // entries per node, a multiple of 32 (0: no near table)
 };
 
 }  // namespace cb200

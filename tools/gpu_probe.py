@@ -53,5 +53,6 @@ main = ['ingest', 'explore_first', 'components', 'solve', 'explore_regrow', 'pat
 tot = sum(ph[k] for k in main)
 print('  phases (cycles/shot of thread 0, group=%s): ' % groups[0] + ', '.join('%s %.0f (%.0f%%)' % (k, v / max(ph['shots'], 1), 100.0 * v / max(tot, 1)) for k, v in ph.items() if k in main))
 print('  solve split (cycles/shot): closed-form %.0f, per-warp blossoms %.0f, block-wide blossoms %.0f' % tuple(ph[k] / max(ph['shots'], 1) for k in ['solve_closed_form', 'solve_warp_blossoms', 'solve_block_blossoms']))
+print('  near-table queries/shot %.0f' % (ph['near_queries'] / max(ph['shots'], 1)))
 print('  balls/shot %.0f, pops/ball %.2f, nodes/ball %.1f, cycles/ball %.0f, cycles/pop %.0f' % (ph['balls'] / max(ph['shots'], 1), ph['ball_pops'] / max(ph['balls'], 1), ph['ball_nodes'] / max(ph['balls'], 1), ph['ball_cycles'] / max(ph['balls'], 1), ph['ball_cycles'] / max(ph['ball_pops'], 1)))
 print('  blossoms per shot / cycles each: ' + ', '.join('%s: %.1f x %.0f' % (b, ph['n_' + b] / max(ph['shots'], 1), ph['blossom_' + b] / max(ph['n_' + b], 1)) for b in ['le8', 'le16', 'le32', 'gt32']))
