@@ -68,7 +68,7 @@ constexpr uint32_t SCAN_TMP = 1024;      // group sizes up to 1024 threads
 
 struct NbEntry {
     uint32_t ev;   // event index within the shot
-    uint32_t pad;
+    uint32_t pos;  // position of the event's node in the near-table row of the list's owner (NO_INDEX: found by a search)
     int64_t d;     // exact shortest-path distance
 };
 
@@ -610,7 +610,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
             if (lane == 0) {
                 const uint32_t w = words[det >> 5];
                 found[0].ev = 2 * (word_rank[det >> 5] + popc32(w & ((1u << (det & 31)) - 1))) + (node & 1);
-                found[0].pad = 0;
+                found[0].pos = NO_INDEX;
                 found[0].d = cand;
             }
             nfound = 1;
@@ -655,7 +655,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
                 }
                 if (lane == 0) {
                     found[nfound].ev = 2 * (word_rank[det >> 5] + popc32(w & ((1u << (det & 31)) - 1))) + (u & 1);
-                    found[nfound].pad = 0;
+                    found[nfound].pos = NO_INDEX;
                     found[nfound].d = d;
                 }
                 nfound++;
@@ -746,6 +746,9 @@ CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry 
 // (tables.h), so a ball query is a scan of the row against the shot's event bits. Both routines return false when the
 // row ends before the query is decided; the caller then runs the Dijkstra search, which gives the same answer.
 // ---------------------------------------------------------------------------------------------------------------
+struct alignas(16) U4 {
+    uint32_t x, y, z, w;
+};
 CB_HD const NearEntry *near_at(const TablesView &T, uint32_t node, uint32_t p) {
     return T.near + ((uint64_t)(p >> 5) * T.num_nodes + node) * 32 + (p & 31);
 }
@@ -828,7 +831,7 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
             const uint32_t node = e.node_pred & 0xFFFFFFu, det = node >> 1;
             NbEntry out;
             out.ev = 2 * (word_rank[det >> 5] + popc32(words[det >> 5] & ((1u << (det & 31)) - 1))) + (node & 1);
-            out.pad = 0;
+            out.pos = p;
             out.d = (int64_t)(e.dist_flag & 0x7FFFFFFFu);
             dst[run + popc32(evs & lane_lt)] = out;
         }
@@ -887,6 +890,54 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
         s.R[i] = limit;
     }
     g.wsync();
+}
+
+// First round: the nearest event of every event, one THREAD per event. Each thread walks its near-table row two
+// entries (16 bytes) at a time until it meets an event; the one-entry neighbour lists live in one block of the dynamic
+// region (entry i belongs to event i). Events whose row holds no event are left with nb_cnt == 0 for explore_event.
+template <class G>
+CB_HDN void explore_first_near(Shot &s, const G &g) {
+    const uint32_t M = s.M, stride = s.T.near_stride;
+    if (g.tid == 0) {
+        uint8_t *mem = stride ? s.alloc(uint64_t{M} * sizeof(NbEntry)) : nullptr;
+        s.hdr->bcast = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
+    }
+    g.sync();
+    const uint32_t base = s.hdr->bcast;
+    g.sync();
+    if (!base) return;
+    NbEntry *const lists = (NbEntry *)(s.dyn + ((uint64_t)(base - 1) << 4));
+    const uint32_t *const words = s.words;
+    for (uint32_t i = (uint32_t)g.tid; i < M; i += (uint32_t)g.n) {
+        const uint32_t src = s.event_node(i);
+        for (uint32_t p = 0; p < stride; p += 2) {
+            const U4 pair = *(const U4 *)near_at(s.T, src, p);  // rows are 256-byte aligned, p is even
+            const NearEntry e[2] = {{pair.x, pair.y}, {pair.z, pair.w}};
+            bool stop = false;
+            for (int k = 0; k < 2 && !stop; k++) {
+                if (e[k].dist_flag == NEAR_PAD) {
+                    stop = true;  // the row ends without an event: the search decides (it reports an exhausted graph)
+                    break;
+                }
+                const uint32_t node = e[k].node_pred & 0xFFFFFFu, det = node >> 1;
+                const uint32_t w = words[det >> 5];
+                if ((w >> (det & 31)) & 1) {
+                    NbEntry out;
+                    out.ev = 2 * (s.word_rank[det >> 5] + popc32(w & ((1u << (det & 31)) - 1))) + (node & 1);
+                    out.pos = p + (uint32_t)k;
+                    out.d = (int64_t)(e[k].dist_flag & 0x7FFFFFFFu);
+                    lists[i] = out;
+                    s.regrown[i] = 1;
+                    s.nb_off[i] = base - 1 + i;
+                    s.nb_cnt[i] = 1;
+                    s.R[i] = out.d;
+                    stop = true;
+                }
+            }
+            if (stop) break;
+        }
+    }
+    g.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1658,7 +1709,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         s.used_flag[i] = 0;
     }
     g.sync();
-    for (uint32_t i = g.warp; i < M; i += g.nwarps) explore_event(s, g, i, -1, 0);
+    explore_first_near(s, g);
+    for (uint32_t i = g.warp; i < M; i += g.nwarps)
+        if (s.nb_cnt[i] == 0) explore_event(s, g, i, -1, 0);
     uint32_t round = 0;
     while (true) {
         g.sync();
@@ -1784,6 +1837,28 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 // to the smallest-id tight predecessor. Stored as the node
 // sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
+// Writes the path src .. dst of event i's matched pair, dst being entry `at` of src's near-table row: a direct edge if
+// the entry is flagged, otherwise the chain of stored canonical predecessors. One thread.
+CB_HDN void near_path_emit(Shot &s, uint32_t i, uint32_t src, uint32_t dst, uint32_t at, bool chunked) {
+    const NearEntry last = *near_at(s.T, src, at);
+    uint32_t len = 2;
+    if (!(last.dist_flag & 0x80000000u))
+        for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; q = near_at(s.T, src, q)->node_pred >> 24) len++;
+    uint32_t *out = (uint32_t *)(chunked ? s.alloc_small(uint64_t{len} * 4) : s.alloc(uint64_t{len} * 4));
+    if (!out) return;
+    out[0] = src;
+    out[len - 1] = dst;
+    uint32_t k = len - 2;
+    if (len > 2)
+        for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; k--) {
+            const uint32_t np = near_at(s.T, src, q)->node_pred;
+            out[k] = np & 0xFFFFFFu;
+            q = np >> 24;
+        }
+    s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
+    s.path_len[i] = len;
+}
+
 // Path of a matched pair from the near table of `src`: find `dst` in the row, then follow the stored canonical
 // predecessors. Returns false when dst is not in the row (the caller searches instead).
 template <class G>
@@ -1804,26 +1879,7 @@ CB_HDN bool extract_path_near(Shot &s, const G &g, uint32_t i, uint32_t src, uin
         if (g.ballot(pad || d > d_total)) return false;
     }
     if (at == NO_INDEX) return false;
-    if (lane == 0) {
-        const NearEntry last = *near_at(s.T, src, at);
-        uint32_t len = 2;
-        if (!(last.dist_flag & 0x80000000u))
-            for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; q = near_at(s.T, src, q)->node_pred >> 24) len++;
-        uint32_t *out = (uint32_t *)s.alloc_small(uint64_t{len} * 4);
-        if (out) {
-            out[0] = src;
-            out[len - 1] = dst;
-            uint32_t k = len - 2;
-            if (len > 2)
-                for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; k--) {
-                    const uint32_t np = near_at(s.T, src, q)->node_pred;
-                    out[k] = np & 0xFFFFFFu;
-                    q = np >> 24;
-                }
-            s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
-            s.path_len[i] = len;
-        }
-    }
+    if (lane == 0) near_path_emit(s, i, src, dst, at, true);
     g.wsync();
     return true;
 }
@@ -1947,10 +2003,28 @@ template <class G>
 CB_HDN void paths_shot(Shot &s, const G &g) {
     for (uint32_t i = g.tid; i < s.M; i += g.n) s.path_len[i] = 0;
     g.sync();
+    // Pairs whose smaller event knows where the partner sits in its near-table row: one thread each.
     uint64_t wsum = 0;
+    for (uint32_t i = (uint32_t)g.tid; i < s.M; i += (uint32_t)g.n) {
+        const int32_t j = s.partner[i];
+        if (j <= (int32_t)i) continue;
+        const NbEntry *l = nb_list(s, i);
+        for (uint32_t k = 0; k < s.nb_cnt[i]; k++)
+            if (l[k].ev == (uint32_t)j) {
+                if (l[k].pos != NO_INDEX) {
+                    wsum += (uint64_t)l[k].d;
+                    near_path_emit(s, i, s.event_node(i), s.event_node((uint32_t)j), l[k].pos, false);
+                }
+                break;
+            }
+    }
+    if (wsum) cb_atomic_add64(&s.hdr->weight, wsum);
+    g.sync();
+    // The rest (seen only from the partner's side, or found by a search): one warp each.
+    wsum = 0;
     for (uint32_t i = g.warp; i < s.M; i += g.nwarps) {
         int32_t j = s.partner[i];
-        if (j > (int32_t)i) {
+        if (j > (int32_t)i && s.path_len[i] == 0) {
             int64_t d = seen_distance(s, i, (uint32_t)j);
             wsum += (uint64_t)d;
             extract_path(s, g, i, (uint32_t)j, d);

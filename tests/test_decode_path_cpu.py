@@ -35,6 +35,30 @@ def test_device_logic_matches_oracle(built, name, shots):
     assert int((obs != o_obs).sum()) <= max(1, shots // 300)
 
 
+@pytest.mark.parametrize('stride', [0, 32, 64])
+@pytest.mark.parametrize('name,shots', [('midout_color_code_d5_r10_p1000', 600), ('color2surface_d7_phenom_r7_p100', 200),
+                                        ('rep_code_rg_d9_transit_p10', 400)])
+def test_near_table_sizes_give_identical_results(built, monkeypatch, name, shots, stride):
+    """Short near-table rows (and none at all) send ball queries and paths to the Dijkstra search: same answers."""
+    text = read_dem(name)
+    dets, _ = NumpyDemSampler(text).sample(shots, seed=4)
+    full = SimDecoder(text).decode(dets, want_edges=False)
+    monkeypatch.setenv('CB200_NEAR_STRIDE', str(stride))
+    short = SimDecoder(text).decode(dets)
+    monkeypatch.delenv('CB200_NEAR_STRIDE')
+    assert (short[2] == 0).all() and (full[2] == 0).all()
+    assert (short[0] == full[0]).all() and (short[1] == full[1]).all()
+    o_obs, o_w = oracle.OracleDecoder(text).decode_batch(dets)
+    assert (short[1] == o_w).all()
+    one = SimDecoder(text)
+    for row in dets[:40]:
+        a = one.decode(row, want_edges=True)
+        monkeypatch.setenv('CB200_NEAR_STRIDE', str(stride))
+        b = SimDecoder(text).decode(row, want_edges=True)
+        monkeypatch.delenv('CB200_NEAR_STRIDE')
+        assert (a[4] == b[4]).all(), 'matched edge lists must not depend on the near-table size'
+
+
 def test_device_logic_survives_tiny_scratch(built):
     """Scratch overflow is reported per shot (status 1), never silently wrong."""
     text = read_dem('midout_color_code_d5_r10_p1000')
