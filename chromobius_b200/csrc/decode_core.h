@@ -1643,48 +1643,62 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
     Blossom<G> &bl = *Blossom<G>::place((uint8_t *)(uintptr_t)off);
     if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
     g.wsync();
-    if (g.lane != 0) {
-        if (bl.par) bl.worker_loop(g);
-        return;
-    }
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
-    for (uint32_t a = 0; a < n; a++) s.lidx[mem[a]] = a + 1;
-    for (uint32_t k = 0; k < (n + 1) * (n + 1); k++) bl.W[k] = 0;
-    // only pairs inside the component take part; pairs seen across components are guarded by the dual check
+    // Set-up by all lanes: the weight matrix from the members' neighbour lists (global memory, one member per lane).
+    // Only pairs inside the component take part; pairs seen across components are guarded by the dual check.
+    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    int64_t *const W = bl.W;
+    for (uint32_t k = lane; k < (n + 1) * (n + 1); k += lanes) W[k] = 0;
+    for (uint32_t a = lane; a < n; a += lanes) s.lidx[mem[a]] = a + 1;
+    g.wsync();
     int64_t big = 2;
-    for (uint32_t a = 0; a < n; a++) {
+    for (uint32_t a = lane; a < n; a += lanes) {
         const NbEntry *l = nb_list(s, mem[a]);
-        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++)
+        const uint32_t cnt = s.nb_cnt[mem[a]];
+        for (uint32_t k = 0; k < cnt; k++)
             if (s.root[l[k].ev] == r && l[k].d + 2 > big) big = l[k].d + 2;
     }
-    for (uint32_t a = 0; a < n; a++) {
+    big = (int64_t)(~g.min64(~(uint64_t)big));  // maximum over the lanes
+    for (uint32_t a = lane; a < n; a += lanes) {
         const NbEntry *l = nb_list(s, mem[a]);
-        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++) {
+        const uint32_t cnt = s.nb_cnt[mem[a]];
+        for (uint32_t k = 0; k < cnt; k++) {
             if (s.root[l[k].ev] != r) continue;
-            uint32_t b = s.lidx[l[k].ev];
-            bl.w((int)a + 1, (int)b) = big - l[k].d;
-            bl.w((int)b, (int)a + 1) = big - l[k].d;
+            const uint32_t b = s.lidx[l[k].ev];
+            W[(a + 1) * (n + 1) + b] = big - l[k].d;  // a pair seen from both sides writes the same value twice
+            W[b * (n + 1) + (a + 1)] = big - l[k].d;
         }
     }
-    int pairs = bl.solve(g);
-    bl.release_workers(g);
-    if (s.prof) {
-        int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
-        cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
-        cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
+    g.wsync();
+    uint32_t pairs = 0;
+    if (lane == 0) {
+        pairs = (uint32_t)bl.solve(g);
+        bl.release_workers(g);
+        if (s.prof) {
+            int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
+            cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
+            cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
+        }
+        if (bl.broken) pairs = NO_INDEX;
+    } else if (bl.par) {
+        bl.worker_loop(g);
     }
-    if (bl.broken) {
-        s.fail(SHOT_SCRATCH_OVERFLOW);
+    g.wsync();
+    pairs = g.shfl32(pairs, 0);
+    if (pairs == NO_INDEX) {
+        if (lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
-    if ((uint32_t)pairs * 2 != n) {
-        for (uint32_t a = 0; a < n; a++) {
+    // Write-back by all lanes, one member each.
+    if (pairs * 2 != n) {
+        for (uint32_t a = lane; a < n; a += lanes) {
             s.solved[mem[a]] = 0;
             if (!bl.match[a + 1]) request_growth(s, mem[a], -1);
         }
+        g.wsync();
         return;
     }
-    for (uint32_t a = 0; a < n; a++) {
+    for (uint32_t a = lane; a < n; a += lanes) {
         uint32_t e = mem[a];
         int64_t need = big - bl.lab[a + 1];  // = 2 * y_a
         s.h[e] = need;
@@ -1693,6 +1707,7 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
         s.partner[e] = (int32_t)mem[bl.match[a + 1] - 1];
         if (need > s.R[e]) request_growth(s, e, need);
     }
+    g.wsync();
 }
 
 template <class G>
@@ -1788,34 +1803,58 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         g.sync();
         pt.lap(8);
         const uint32_t nbig = s.hdr->nbig;
-        // blossom components that fit a warp's shared-memory table space: one warp each, in parallel
-        bool dirtied_shared = false;
-        for (uint32_t k = g.warp; k < nbig; k += g.nwarps) {
-            uint32_t c = s.uf[k];
-            if (s.sh_ball.H && Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[c]]) > s.sh_ball.raw_bytes && g.nwarps > 1) {
-                if (g.lane == 0) s.lidx_huge()[cb_atomic_add(&s.hdr->nhuge, 1)] = c;
-                continue;
+        // Blossom components share the group's shared-memory table space as one pool: largest first, each gets its own
+        // slice, and what does not fit next to the others waits for the next wave (components beyond the whole pool use
+        // the dynamic region). s.uf holds the components, s.fillp their (wave << 16 | offset / 16); both are free here.
+        if (nbig) {
+            if (g.tid == 0) {
+                for (uint32_t a = 1; a < nbig; a++) {  // insertion sort: (size descending, root ascending)
+                    const uint32_t v = s.uf[a], vn = s.cnt[s.comp_root[v]], vr = s.comp_root[v];
+                    uint32_t b = a;
+                    while (b > 0) {
+                        const uint32_t u = s.uf[b - 1], un = s.cnt[s.comp_root[u]];
+                        if (un > vn || (un == vn && s.comp_root[u] < vr)) break;
+                        s.uf[b] = u;
+                        b--;
+                    }
+                    s.uf[b] = v;
+                }
+                const uint64_t pool = s.sh_ball.H ? s.sh_tables_bytes : 0;
+                uint32_t wave = 0;
+                uint64_t top = 0;
+                for (uint32_t k = 0; k < nbig; k++) {
+                    const uint64_t need = align16(Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[s.uf[k]]]));
+                    if (need > pool) {
+                        s.fillp[k] = (wave << 16) | 0xFFFFu;
+                        continue;
+                    }
+                    if (top + need > pool) {
+                        wave++;
+                        top = 0;
+                    }
+                    s.fillp[k] = (wave << 16) | (uint32_t)(top >> 4);
+                    top += need;
+                }
+                s.hdr->bcast = wave + 1;
             }
-            solve_component_blossom(s, g, c, s.sh_ball.H ? s.sh_ball.raw : nullptr, s.sh_ball.raw_bytes);
-            g.wsync();
-            dirtied_shared = true;
-        }
-        g.sync();
-        pt.lap(9);
-        // the few components that do not: one after the other on warp 0, in the whole block's table space
-        const uint32_t nhuge = s.hdr->nhuge;
-        if (nhuge) {
-            if (g.warp == 0)
-                for (uint32_t k = 0; k < nhuge; k++) {
-                    solve_component_blossom(s, g, s.lidx_huge()[k], s.sh_tables, s.sh_tables_bytes);
+            g.sync();
+            const uint32_t nwaves = s.hdr->bcast;
+            uint32_t k0 = 0;
+            for (uint32_t wave = 0; wave < nwaves; wave++) {
+                uint32_t k1 = k0;
+                while (k1 < nbig && (s.fillp[k1] >> 16) == wave) k1++;
+                for (uint32_t k = k0 + g.warp; k < k1; k += g.nwarps) {
+                    const uint32_t off16 = s.fillp[k] & 0xFFFFu;
+                    const uint64_t need = Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[s.uf[k]]]);
+                    solve_component_blossom(s, g, s.uf[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4), need);
                     g.wsync();
                 }
-            dirtied_shared = true;
-            g.sync();
-        }
-        if (dirtied_shared && s.sh_ball.H) {
-            g.wsync();
-            for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
+                k0 = k1;
+                g.sync();
+            }
+            pt.lap(9);
+            if (s.sh_ball.H)
+                for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
         }
         g.sync();
         pt.lap(10);
