@@ -1079,18 +1079,16 @@ struct Blossom {
             }
         }
     }
-    // max W, reduced across lanes by the caller
-    CB_HD int64_t k_wmax(int lane, int lanes) {
-        int64_t w_max = 0;
-        for (int u = 1 + lane; u <= n; u += lanes)
+    // Starting labels: lab[u] = max_v W[u][v], feasible because lab[u] + lab[v] >= 2 W[u][v] for every edge.
+    CB_HD void k_row_max_lab(int lane, int lanes) {
+        for (int u = 1 + lane; u <= n; u += lanes) {
+            int64_t m = 0;
             for (int v = 1; v <= n; ++v) {
                 int64_t x = W[u * (n + 1) + v];
-                if (x > w_max) w_max = x;
+                if (x > m) m = x;
             }
-        return w_max;
-    }
-    CB_HD void k_set_lab(int lane, int lanes, int64_t v) {
-        for (int u = 1 + lane; u <= n; u += lanes) lab[u] = v;
+            lab[u] = m;
+        }
     }
     // (distance << 16 | u) of the best eligible vertex for slack[x]; ~0 when none. Lowest u wins ties.
     CB_HD uint64_t k_set_slack(int lane, int lanes, int x) {
@@ -1162,13 +1160,11 @@ struct Blossom {
         const int lane = g.lane, lanes = g.lanes;
         uint64_t r = 0;
         switch (op) {
-            case OP_INIT: {
+            case OP_INIT:
                 k_init(lane, lanes);
-                int64_t wm = (int64_t)(~g.min64(~(uint64_t)k_wmax(lane, lanes)));  // max via min of complements
-                g.wsync();
-                k_set_lab(lane, lanes, wm);
+                g.wsync();  // k_init clears lab[] with a different lane-to-vertex mapping
+                k_row_max_lab(lane, lanes);
                 break;
-            }
             case OP_SET_SLACK:
                 r = g.min64(k_set_slack(lane, lanes, (int)a0));
                 break;
@@ -1480,9 +1476,29 @@ struct Blossom {
             call(g, OP_INIT);
         } else {
             k_init(0, 1);
-            k_set_lab(0, 1, k_wmax(0, 1));
+            k_row_max_lab(0, 1);
         }
+        // Greedy start on the edges that are tight under the row-maximum labels (mutual best partners), lowest indices
+        // first: a valid primal-dual state that leaves only the remaining vertices to the augmentation phases.
         int cnt = 0;
+        for (int u = 1; u <= n; ++u) {
+            if (match[u] || lab[u] <= 0) continue;
+            bool done = false;
+            for (int k = 0; k < AW && !done; ++k) {
+                uint32_t bits = adjm[u * AW + k];
+                while (bits) {
+                    int v = 32 * k + (int)ctz32(bits);
+                    bits &= bits - 1;
+                    if (!match[v] && W[u * (n + 1) + v] == lab[u] && lab[v] == lab[u]) {
+                        match[u] = (uint16_t)v;
+                        match[v] = (uint16_t)u;
+                        ++cnt;
+                        done = true;
+                        break;
+                    }
+                }
+            }
+        }
         while (matching(g)) ++cnt;
         return cnt;
     }

@@ -1060,8 +1060,27 @@ struct DenseBlossom {
                 flower_from[u][v] = (u == v ? u : 0);
                 w_max = std::max(w_max, g[u][v].w);
             }
-        for (int u = 1; u <= n; ++u) lab[u] = w_max;
+        (void)w_max;
+        // Start from per-vertex labels lab[u] = max_v w(u, v) (feasible: lab[u] + lab[v] >= 2 w(u, v)) and a greedy
+        // matching on the edges that are tight under them (mutual best partners), lowest indices first. Any feasible
+        // start with tight matched edges is a valid state of the primal-dual method; this one leaves only the
+        // vertices without a mutual best partner to the augmentation phases. (decode_core.h Blossom::solve does the same.)
+        for (int u = 1; u <= n; ++u) {
+            int64_t m = 0;
+            for (int v = 1; v <= n; ++v) m = std::max(m, g[u][v].w);
+            lab[u] = m;
+        }
         int cnt = 0;
+        for (int u = 1; u <= n; ++u) {
+            if (match[u] || lab[u] <= 0) continue;
+            for (int v = 1; v <= n; ++v)
+                if (v != u && !match[v] && g[u][v].w == lab[u] && lab[v] == lab[u]) {
+                    match[u] = v;
+                    match[v] = u;
+                    ++cnt;
+                    break;
+                }
+        }
         while (matching()) ++cnt;
         return cnt;
     }
