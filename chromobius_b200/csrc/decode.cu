@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict_
 }
 
 // K2: the decode kernel. Persistent groups pull shots from a queue.
+#ifndef CB_MIN_BLOCKS_256
+#define CB_MIN_BLOCKS_256 3
+#endif
 template <int GROUP>
-__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? 3 : 6))
+__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? CB_MIN_BLOCKS_256 : 6))
     k_decode(DecodeParams p, uint32_t num_groups, uint32_t smem_per_group) {
     uint32_t group, gib;
     DevGroup<GROUP> g;
@@ -237,7 +240,7 @@ struct cb200_decoder {
     DeviceBuf<float> d_wfloat;
     // arena layout currently initialised on the device
     // tuning
-    uint32_t tune_group = 0, tune_ht_log2 = 0;
+    uint32_t tune_group = 0, tune_ht_log2 = 0, tune_pool_bytes = 24u << 10;
 };
 
 namespace {
@@ -375,9 +378,15 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     pl.group = group;
     uint32_t full = 4;
     while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
-    uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : 8;
+    // With a near table the Dijkstra search is a rare fallback and runs in the global tables; shared memory then only
+    // holds the shot's row and the blossom scratch pool, which leaves most of the SM's unified storage to the L1 cache
+    // (the per-event arrays of the shots in flight live there). Without a near table every ball is a search: shared tables.
+    const bool near = d->host.near_stride != 0;
+    uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : (near ? 0 : 8);
     uint32_t gl = std::min<uint32_t>(full, 14 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
+    pl.cfg.sh_pool = near ? d->tune_pool_bytes : 0;
+    if (const char *env = getenv("CB200_POOL_KB")) pl.cfg.sh_pool = near ? (uint32_t)strtoul(env, nullptr, 10) << 10 : 0;  // experiments
     pl.cfg.sh_found = 16;
     pl.cfg.ht_log2 = gl;
     pl.cfg.found_cap = 256u << (2 * escalation);

@@ -43,6 +43,13 @@
 #define CB_HDN inline
 #endif
 
+// The sequential blossom code is latency bound and large; unrolled loops only make it miss the instruction cache.
+#ifdef __CUDACC__
+#define CB_LOOP _Pragma("unroll 1")
+#else
+#define CB_LOOP
+#endif
+
 namespace cb200 {
 
 // Per-shot status codes (status_out). 0 = decoded.
@@ -79,7 +86,7 @@ struct ScratchConfig {
     uint32_t ht_log2;     // global-memory fallback table slots per warp = 1 << ht_log2
     uint32_t found_cap;   // events a ball may report from the fallback attempt
     uint32_t max_events;  // matcher events (2 x detection events) per shot the arena is sized for
-    uint32_t pad;
+    uint32_t sh_pool;     // bytes of shared memory for blossom scratch (shares its space with the shared ball tables)
     uint64_t dyn_bytes;   // dynamic region (neighbour lists, blossom scratch, paths, Euler arrays)
 };
 
@@ -257,7 +264,8 @@ CB_HD uint64_t event_bytes(const ScratchConfig &c) {
 }
 CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets, uint32_t nwarps) {
     uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
-    return align16(nwords * 4) + align16((nwords + 1) * 4) + nwarps * ball_table_bytes(c.sh_ht_log2, c.sh_found);
+    uint64_t tables = nwarps * ball_table_bytes(c.sh_ht_log2, c.sh_found), pool = align16(c.sh_pool);
+    return align16(nwords * 4) + align16((nwords + 1) * 4) + (tables > pool ? tables : pool);
 }
 CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t nwarps) {
     return align16(sizeof(GroupHeader)) + align16(SCAN_TMP * 4) + nwarps * ball_table_bytes(c.ht_log2, c.found_cap) +
@@ -272,7 +280,7 @@ struct Shot {
     GroupHeader *hdr;
     uint32_t *scan_tmp;    // [SCAN_TMP]
     BallTables sh_ball;    // this warp's shared-memory tables (H == 0: none)
-    uint8_t *sh_tables;    // all warps' shared-memory tables, contiguous (scratch for large blossoms)
+    uint8_t *sh_tables;    // all warps' shared-memory tables, contiguous: the blossom scratch pool between ball phases
     uint64_t sh_tables_bytes;
     BallTables gl_ball;    // this warp's global-memory fallback tables
     uint32_t *node_slot;   // [num_nodes] persistent-clean
@@ -389,6 +397,7 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, p.cfg.sh_ht_log2, p.cfg.sh_found);
     s.sh_tables = sh;
     s.sh_tables_bytes = (uint64_t)g.nwarps * sb;
+    if (align16(p.cfg.sh_pool) > s.sh_tables_bytes) s.sh_tables_bytes = align16(p.cfg.sh_pool);
 }
 
 // Called once per group before the first shot of a launch (shared memory does not survive launches).
@@ -956,30 +965,84 @@ CB_HDN void explore_first_near(Shot &s, const G &g) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BLOSSOM_PAR_MIN = 12;  // components with at least this many events use the warp helpers
 
-template <class G>
+template <class G, int CAP = 0>
 struct Blossom {
     enum Op : uint32_t { OP_EXIT = 0, OP_INIT, OP_SET_SLACK, OP_DUAL_MIN, OP_LAB_UPDATE, OP_NEXT_TIGHT, OP_BLOSSOM_CLEAR, OP_MERGE_ROW, OP_PHASE_INIT };
     int n, n_x, NX, FL, AW;
-    int64_t *W;        // (n+1) x (n+1)
-    uint8_t *ge;       // NX x NX x 2 : original endpoints (eu, ev) of the best edge between two nodes; eu == 0: none
-    int64_t *lab;      // NX
-    uint16_t *match, *slack, *st, *pa;
-    int8_t *S;
-    uint32_t *vis;
-    uint16_t *ff;      // flower_from: NX x (n+1)
-    uint16_t *fl;      // flower lists: (NX - n) x FL, row b - n
-    uint16_t *fl_len;  // NX
-    uint16_t *q;       // circular queue, capacity QC
-    uint16_t *stk;     // explicit stack, capacity 2*NX
-    uint32_t *adjm;    // (n+1) x AW adjacency bit rows: bit v of row u <=> W[u][v] > 0
-    uint32_t *cmd;     // [8] command block (master -> workers)
+    // Storage. CAP == 0: sized for n at run time, addressed through the pointers below (any memory). CAP > 0: sized for CAP
+    // vertices at compile time, every array at a constant offset from the object itself, which then always lives in shared
+    // memory: the accessors below turn into shared-memory loads with immediate offsets.
+    int64_t *W_p;        // (n+1) x (n+1)
+    uint8_t *ge_p;       // NX x NX x 2 : original endpoints (eu, ev) of the best edge between two nodes; eu == 0: none
+    int64_t *lab_p;      // NX
+    uint16_t *match_p, *slack_p, *st_p, *pa_p;
+    int8_t *S_p;
+    uint32_t *vis_p;
+    uint16_t *ff_p;      // flower_from: NX x (n+1)
+    uint16_t *fl_p;      // flower lists: (NX - n) x FL, row b - n
+    uint16_t *fl_len_p;  // NX
+    uint16_t *q_p;       // circular queue, capacity QC
+    uint16_t *stk_p;     // explicit stack, capacity 2*NX
+    uint32_t *adjm_p;    // (n+1) x AW adjacency bit rows: bit v of row u <=> W[u][v] > 0
+    uint32_t *cmd_p;     // [8] command block (master -> workers)
     int qh, qt, QC;
     uint32_t vis_t;
     bool broken;
     bool par;
     bool wide;         // endpoints stored as u16
 
+    static constexpr uint32_t c16(uint64_t x) { return (uint32_t)((x + 15) & ~uint64_t{15}); }
+    static constexpr int NXC = CAP + CAP / 2 + 2, WSC = CAP + 1, FLC = CAP + 2, QCC = 2 * CAP + 4, AWC = (CAP + 32) / 32;
+    static constexpr uint32_t HDR = 256;  // room for the object itself (checked below the class)
+    static constexpr uint32_t OFF_W = HDR;
+    static constexpr uint32_t OFF_GE = OFF_W + c16(uint64_t(WSC) * WSC * 8);
+    static constexpr uint32_t OFF_LAB = OFF_GE + c16(uint64_t(NXC) * NXC * 2);
+    static constexpr uint32_t OFF_MATCH = OFF_LAB + c16(uint64_t(NXC) * 8);
+    static constexpr uint32_t OFF_SLACK = OFF_MATCH + c16(uint64_t(NXC) * 2);
+    static constexpr uint32_t OFF_ST = OFF_SLACK + c16(uint64_t(NXC) * 2);
+    static constexpr uint32_t OFF_PA = OFF_ST + c16(uint64_t(NXC) * 2);
+    static constexpr uint32_t OFF_S = OFF_PA + c16(uint64_t(NXC) * 2);
+    static constexpr uint32_t OFF_VIS = OFF_S + c16(uint64_t(NXC));
+    static constexpr uint32_t OFF_FF = OFF_VIS + c16(uint64_t(NXC) * 4);
+    static constexpr uint32_t OFF_FL = OFF_FF + c16(uint64_t(NXC) * WSC * 2);
+    static constexpr uint32_t OFF_FLLEN = OFF_FL + c16(uint64_t(CAP / 2 + 2) * FLC * 2);
+    static constexpr uint32_t OFF_Q = OFF_FLLEN + c16(uint64_t(NXC) * 2);
+    static constexpr uint32_t OFF_STK = OFF_Q + c16(uint64_t(QCC) * 2);
+    static constexpr uint32_t OFF_ADJM = OFF_STK + c16(uint64_t(2 * NXC + 4) * 2);
+    static constexpr uint32_t OFF_CMD = OFF_ADJM + c16(uint64_t(WSC) * AWC * 4);
+    static constexpr uint32_t FIXED_BYTES = OFF_CMD + 32;
+    CB_HD uint8_t *self() const { return (uint8_t *)this; }
+    CB_HD int64_t *W() const { return CAP ? (int64_t *)(self() + OFF_W) : W_p; }
+    CB_HD uint8_t *ge() const { return CAP ? self() + OFF_GE : ge_p; }
+    CB_HD int64_t *lab() const { return CAP ? (int64_t *)(self() + OFF_LAB) : lab_p; }
+    CB_HD uint16_t *match() const { return CAP ? (uint16_t *)(self() + OFF_MATCH) : match_p; }
+    CB_HD uint16_t *slack() const { return CAP ? (uint16_t *)(self() + OFF_SLACK) : slack_p; }
+    CB_HD uint16_t *st() const { return CAP ? (uint16_t *)(self() + OFF_ST) : st_p; }
+    CB_HD uint16_t *pa() const { return CAP ? (uint16_t *)(self() + OFF_PA) : pa_p; }
+    CB_HD int8_t *S() const { return CAP ? (int8_t *)(self() + OFF_S) : S_p; }
+    CB_HD uint32_t *vis() const { return CAP ? (uint32_t *)(self() + OFF_VIS) : vis_p; }
+    CB_HD uint16_t *ff() const { return CAP ? (uint16_t *)(self() + OFF_FF) : ff_p; }
+    CB_HD uint16_t *fl() const { return CAP ? (uint16_t *)(self() + OFF_FL) : fl_p; }
+    CB_HD uint16_t *fl_len() const { return CAP ? (uint16_t *)(self() + OFF_FLLEN) : fl_len_p; }
+    CB_HD uint16_t *q() const { return CAP ? (uint16_t *)(self() + OFF_Q) : q_p; }
+    CB_HD uint16_t *stk() const { return CAP ? (uint16_t *)(self() + OFF_STK) : stk_p; }
+    CB_HD uint32_t *adjm() const { return CAP ? (uint32_t *)(self() + OFF_ADJM) : adjm_p; }
+    CB_HD uint32_t *cmd() const { return CAP ? (uint32_t *)(self() + OFF_CMD) : cmd_p; }
+    // row strides / capacities
+    CB_HD int ws() const { return CAP ? WSC : n + 1; }
+    CB_HD int nxs() const { return CAP ? NXC : NX; }
+    CB_HD int fls() const { return CAP ? FLC : FL; }
+    CB_HD int aws() const { return CAP ? AWC : AW; }
+    CB_HD int qcs() const { return CAP ? QCC : QC; }
+    // Tells the compiler the address space of a fixed-layout object (no-op otherwise).
+    CB_HD void in_shared() const {
+#ifdef __CUDA_ARCH__
+        if (CAP) __builtin_assume(__isShared(this));
+#endif
+    }
+
     static CB_HD uint64_t bytes_needed(int n) {
+        if (CAP) return FIXED_BYTES;
         int NX = n + n / 2 + 2;
         int FL = n + 2;
         int AW = (n + 32) / 32;
@@ -1005,96 +1068,104 @@ struct Blossom {
     // line per 4 bytes.
     static CB_HD Blossom *place(uint8_t *mem) { return (Blossom *)mem; }
     CB_HD void bind(uint8_t *mem, int n_, int lanes) {
-        mem += align16(sizeof(Blossom));
         n = n_;
         NX = n + n / 2 + 2;
         FL = n + 2;
         QC = 2 * n + 4;
         AW = (n + 32) / 32;
-        uint8_t *p = mem;
-        wide = n > (int)NARROW_COMPONENT;
-        W = (int64_t *)p; p += align16(uint64_t(n + 1) * (n + 1) * 8);
-        ge = p; p += align16(uint64_t(NX) * NX * 2 * (wide ? 2 : 1));
-        lab = (int64_t *)p; p += align16(uint64_t(NX) * 8);
-        match = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
-        slack = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
-        st = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
-        pa = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
-        S = (int8_t *)p; p += align16(uint64_t(NX));
-        vis = (uint32_t *)p; p += align16(uint64_t(NX) * 4);
-        ff = (uint16_t *)p; p += align16(uint64_t(NX) * (n + 1) * 2);
-        fl = (uint16_t *)p; p += align16(uint64_t(NX - n) * FL * 2);
-        fl_len = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
-        q = (uint16_t *)p; p += align16(uint64_t(QC) * 2);
-        stk = (uint16_t *)p; p += align16(uint64_t(2 * NX + 4) * 2);
-        adjm = (uint32_t *)p; p += align16(uint64_t(n + 1) * AW * 4);
-        cmd = (uint32_t *)p;
+        wide = !CAP && n > (int)NARROW_COMPONENT;
         broken = false;
         par = lanes > 1 && n >= BLOSSOM_PAR_MIN;
         n_x = n;
+        if (CAP) return;
+        uint8_t *p = mem + align16(sizeof(Blossom));
+        W_p = (int64_t *)p; p += align16(uint64_t(n + 1) * (n + 1) * 8);
+        ge_p = p; p += align16(uint64_t(NX) * NX * 2 * (wide ? 2 : 1));
+        lab_p = (int64_t *)p; p += align16(uint64_t(NX) * 8);
+        match_p = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        slack_p = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        st_p = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        pa_p = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        S_p = (int8_t *)p; p += align16(uint64_t(NX));
+        vis_p = (uint32_t *)p; p += align16(uint64_t(NX) * 4);
+        ff_p = (uint16_t *)p; p += align16(uint64_t(NX) * (n + 1) * 2);
+        fl_p = (uint16_t *)p; p += align16(uint64_t(NX - n) * FL * 2);
+        fl_len_p = (uint16_t *)p; p += align16(uint64_t(NX) * 2);
+        q_p = (uint16_t *)p; p += align16(uint64_t(QC) * 2);
+        stk_p = (uint16_t *)p; p += align16(uint64_t(2 * NX + 4) * 2);
+        adjm_p = (uint32_t *)p; p += align16(uint64_t(n + 1) * AW * 4);
+        cmd_p = (uint32_t *)p;
     }
-    CB_HD int64_t &w(int u, int v) { return W[u * (n + 1) + v]; }
-    CB_HD int geu(int a, int b) const { return wide ? ((const uint16_t *)ge)[(a * NX + b) * 2] : ge[(a * NX + b) * 2]; }
-    CB_HD int gev(int a, int b) const { return wide ? ((const uint16_t *)ge)[(a * NX + b) * 2 + 1] : ge[(a * NX + b) * 2 + 1]; }
+    CB_HD int64_t &w(int u, int v) { return W()[u * ws() + v]; }
+    CB_HD bool is_wide() const { return !CAP && wide; }
+    CB_HD int geu(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2] : ge()[(a * nxs() + b) * 2]; }
+    CB_HD int gev(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2 + 1] : ge()[(a * nxs() + b) * 2 + 1]; }
     CB_HD bool has(int a, int b) const { return geu(a, b) != 0; }
     CB_HD void set_ge(int a, int b, int eu, int ev) {
-        if (wide) {
-            ((uint16_t *)ge)[(a * NX + b) * 2] = (uint16_t)eu;
-            ((uint16_t *)ge)[(a * NX + b) * 2 + 1] = (uint16_t)ev;
+        if (is_wide()) {
+            ((uint16_t *)ge())[(a * nxs() + b) * 2] = (uint16_t)eu;
+            ((uint16_t *)ge())[(a * nxs() + b) * 2 + 1] = (uint16_t)ev;
         } else {
-            ge[(a * NX + b) * 2] = (uint8_t)eu;
-            ge[(a * NX + b) * 2 + 1] = (uint8_t)ev;
+            ge()[(a * nxs() + b) * 2] = (uint8_t)eu;
+            ge()[(a * nxs() + b) * 2 + 1] = (uint8_t)ev;
         }
     }
     CB_HD int64_t edist(int a, int b) {  // slack of the best edge between nodes a and b
         int eu = geu(a, b), ev = gev(a, b);
-        return lab[eu] + lab[ev] - 2 * W[eu * (n + 1) + ev];
+        return lab()[eu] + lab()[ev] - 2 * W()[eu * ws() + ev];
     }
-    CB_HD uint16_t *flower(int b) { return fl + (b - n) * FL; }
-    CB_HD uint16_t &ffrom(int b, int x) { return ff[b * (n + 1) + x]; }
+    CB_HD uint16_t *flower(int b) { return fl() + (b - n) * fls(); }
+    CB_HD uint16_t &ffrom(int b, int x) { return ff()[b * ws() + x]; }
 
     // ---- data-parallel kernels: executed by every participating lane (`lane`, `lanes` = 0, 1 when running alone) ----
     CB_HD void k_init(int lane, int lanes) {
+        CB_LOOP
         for (int u = lane; u < NX; u += lanes) {
-            match[u] = 0;
-            st[u] = (uint16_t)(u <= n ? u : 0);
-            fl_len[u] = 0;
-            vis[u] = 0;
-            slack[u] = 0;
-            pa[u] = 0;
-            S[u] = -1;
-            lab[u] = 0;
+            match()[u] = 0;
+            st()[u] = (uint16_t)(u <= n ? u : 0);
+            fl_len()[u] = 0;
+            vis()[u] = 0;
+            slack()[u] = 0;
+            pa()[u] = 0;
+            S()[u] = -1;
+            lab()[u] = 0;
         }
+        CB_LOOP
         for (int u = 1 + lane; u <= n; u += lanes) {
-            for (int k = 0; k < AW; k++) adjm[u * AW + k] = 0;
+            CB_LOOP
+            for (int k = 0; k < aws(); k++) adjm()[u * aws() + k] = 0;
+            CB_LOOP
             for (int v = 1; v <= n; ++v) {
                 ffrom(u, v) = (uint16_t)(u == v ? u : 0);
-                int64_t x = W[u * (n + 1) + v];
+                int64_t x = W()[u * ws() + v];
                 if (x > 0) {
                     set_ge(u, v, u, v);
-                    adjm[u * AW + (v >> 5)] |= 1u << (v & 31);
+                    adjm()[u * aws() + (v >> 5)] |= 1u << (v & 31);
                 } else {
                     set_ge(u, v, 0, 0);
                 }
             }
         }
     }
-    // Starting labels: lab[u] = max_v W[u][v], feasible because lab[u] + lab[v] >= 2 W[u][v] for every edge.
+    // Starting labels: lab()[u] = max_v W()[u][v], feasible because lab()[u] + lab()[v] >= 2 W()[u][v] for every edge.
     CB_HD void k_row_max_lab(int lane, int lanes) {
+        CB_LOOP
         for (int u = 1 + lane; u <= n; u += lanes) {
             int64_t m = 0;
+            CB_LOOP
             for (int v = 1; v <= n; ++v) {
-                int64_t x = W[u * (n + 1) + v];
+                int64_t x = W()[u * ws() + v];
                 if (x > m) m = x;
             }
-            lab[u] = m;
+            lab()[u] = m;
         }
     }
-    // (distance << 16 | u) of the best eligible vertex for slack[x]; ~0 when none. Lowest u wins ties.
+    // (distance << 16 | u) of the best eligible vertex for slack()[x]; ~0 when none. Lowest u wins ties.
     CB_HD uint64_t k_set_slack(int lane, int lanes, int x) {
         uint64_t best = ~uint64_t{0};
+        CB_LOOP
         for (int u = 1 + lane; u <= n; u += lanes)
-            if (has(u, x) && st[u] != x && S[st[u]] == 0) {
+            if (has(u, x) && st()[u] != x && S()[st()[u]] == 0) {
                 uint64_t key = ((uint64_t)edist(u, x) << 16) | (uint64_t)u;
                 if (key < best) best = key;
             }
@@ -1102,67 +1173,77 @@ struct Blossom {
     }
     CB_HD uint64_t k_dual_min(int lane, int lanes, int nx) {
         uint64_t d = (uint64_t)(INT64_MAX / 4);
+        CB_LOOP
         for (int b = n + 1 + lane; b <= nx; b += lanes)
-            if (st[b] == b && S[b] == 1) {
-                uint64_t v = (uint64_t)(lab[b] / 2);
+            if (st()[b] == b && S()[b] == 1) {
+                uint64_t v = (uint64_t)(lab()[b] / 2);
                 if (v < d) d = v;
             }
+        CB_LOOP
         for (int x = 1 + lane; x <= nx; x += lanes)
-            if (st[x] == x && slack[x]) {
-                int64_t sd = edist(slack[x], x);
-                if (S[x] == -1) {
+            if (st()[x] == x && slack()[x]) {
+                int64_t sd = edist(slack()[x], x);
+                if (S()[x] == -1) {
                     if ((uint64_t)sd < d) d = (uint64_t)sd;
-                } else if (S[x] == 0) {
+                } else if (S()[x] == 0) {
                     if ((uint64_t)(sd / 2) < d) d = (uint64_t)(sd / 2);
                 }
             }
         return d;
     }
     CB_HD void k_lab_update(int lane, int lanes, int nx, int64_t d) {
+        CB_LOOP
         for (int u = 1 + lane; u <= n; u += lanes) {
-            if (S[st[u]] == 0) lab[u] -= d;
-            else if (S[st[u]] == 1) lab[u] += d;
+            if (S()[st()[u]] == 0) lab()[u] -= d;
+            else if (S()[st()[u]] == 1) lab()[u] += d;
         }
+        CB_LOOP
         for (int b = n + 1 + lane; b <= nx; b += lanes)
-            if (st[b] == b) {
-                if (S[b] == 0) lab[b] += d * 2;
-                else if (S[b] == 1) lab[b] -= d * 2;
+            if (st()[b] == b) {
+                if (S()[b] == 0) lab()[b] += d * 2;
+                else if (S()[b] == 1) lab()[b] -= d * 2;
             }
     }
     CB_HD bool tight_candidate(int x) {
-        return st[x] == x && slack[x] && st[slack[x]] != x && edist(slack[x], x) == 0;
+        return st()[x] == x && slack()[x] && st()[slack()[x]] != x && edist(slack()[x], x) == 0;
     }
     CB_HD void k_blossom_clear(int lane, int lanes, int b, int nx) {
+        CB_LOOP
         for (int x = 1 + lane; x <= nx; x += lanes) {
             set_ge(b, x, 0, 0);
             set_ge(x, b, 0, 0);
         }
+        CB_LOOP
         for (int x = 1 + lane; x <= n; x += lanes) ffrom(b, x) = 0;
     }
     CB_HD void k_merge_row(int lane, int lanes, int b, int xs, int nx) {
+        CB_LOOP
         for (int x = 1 + lane; x <= nx; x += lanes)
             if (has(xs, x) && (!has(b, x) || edist(xs, x) < edist(b, x))) {
                 set_ge(b, x, geu(xs, x), gev(xs, x));
                 set_ge(x, b, geu(x, xs), gev(x, xs));
             }
+        CB_LOOP
         for (int x = 1 + lane; x <= n; x += lanes)
             if (ffrom(xs, x)) ffrom(b, x) = (uint16_t)xs;
     }
     CB_HD void k_phase_init(int lane, int lanes, int nx) {
+        CB_LOOP
         for (int x = 1 + lane; x <= nx; x += lanes) {
-            S[x] = -1;
-            slack[x] = 0;
+            S()[x] = -1;
+            slack()[x] = 0;
         }
     }
 
     // ---- warp dispatch: every lane runs the same helper; results are reduced with warp primitives ----
     CB_HDN uint64_t dispatch(const G &g, uint32_t op, uint32_t a0, uint32_t a1, uint32_t a2) {
+        in_shared();
         const int lane = g.lane, lanes = g.lanes;
         uint64_t r = 0;
         switch (op) {
             case OP_INIT:
                 k_init(lane, lanes);
-                g.wsync();  // k_init clears lab[] with a different lane-to-vertex mapping
+                g.wsync();  // k_init clears lab()[] with a different lane-to-vertex mapping
                 k_row_max_lab(lane, lanes);
                 break;
             case OP_SET_SLACK:
@@ -1178,6 +1259,7 @@ struct Blossom {
                 // smallest x >= a0 that is a tight candidate, or a1 + 1
                 int nx = (int)a1;
                 r = (uint64_t)(nx + 1);
+                CB_LOOP
                 for (int base = (int)a0; base <= nx; base += lanes) {
                     int x = base + lane;
                     uint32_t hits = g.ballot(x <= nx && tight_candidate(x));
@@ -1204,10 +1286,10 @@ struct Blossom {
     }
     // master side: announce, run together, wait for everyone's writes
     CB_HD uint64_t call(const G &g, uint32_t op, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
-        cmd[0] = op;
-        cmd[1] = a0;
-        cmd[2] = a1;
-        cmd[3] = a2;
+        cmd()[0] = op;
+        cmd()[1] = a0;
+        cmd()[2] = a1;
+        cmd()[3] = a2;
         g.wsync();
         uint64_t r = dispatch(g, op, a0, a1, a2);
         g.wsync();
@@ -1215,60 +1297,70 @@ struct Blossom {
     }
     // lanes 1..31
     CB_HDN void worker_loop(const G &g) {
+        in_shared();
+        CB_LOOP
         while (true) {
             g.wsync();
-            uint32_t op = cmd[0];
+            uint32_t op = cmd()[0];
             if (op == OP_EXIT) break;
-            dispatch(g, op, cmd[1], cmd[2], cmd[3]);
+            dispatch(g, op, cmd()[1], cmd()[2], cmd()[3]);
             g.wsync();
         }
     }
     CB_HD void release_workers(const G &g) {
         if (par) {
-            cmd[0] = OP_EXIT;
+            cmd()[0] = OP_EXIT;
             g.wsync();
         }
     }
 
     // ---- sequential bookkeeping (master) ----
     CB_HD void update_slack(int u, int x) {
-        if (!slack[x] || edist(u, x) < edist(slack[x], x)) slack[x] = (uint16_t)u;
+        if (!slack()[x] || edist(u, x) < edist(slack()[x], x)) slack()[x] = (uint16_t)u;
     }
     CB_HDN void set_slack(const G &g, int x) {
+        in_shared();
         uint64_t best = par ? call(g, OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
-        slack[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
+        slack()[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
     }
     CB_HD void q_put(int v) {
-        q[qt] = (uint16_t)v;
-        qt = qt + 1 == QC ? 0 : qt + 1;
+        q()[qt] = (uint16_t)v;
+        qt = qt + 1 == qcs() ? 0 : qt + 1;
         if (qt == qh) broken = true;
     }
     // depth-first, children in order
     CB_HDN void q_push(int x) {
+        in_shared();
         int sp = 0;
-        stk[sp++] = (uint16_t)x;
+        stk()[sp++] = (uint16_t)x;
+        CB_LOOP
         while (sp) {
-            int y = stk[--sp];
+            int y = stk()[--sp];
             if (y <= n) {
                 q_put(y);
                 continue;
             }
             uint16_t *f = flower(y);
-            for (int i = fl_len[y] - 1; i >= 0; --i) stk[sp++] = f[i];
+            CB_LOOP
+            for (int i = fl_len()[y] - 1; i >= 0; --i) stk()[sp++] = f[i];
         }
     }
     CB_HDN void set_st(int x, int b) {
+        in_shared();
         int sp = 0;
-        stk[sp++] = (uint16_t)x;
+        stk()[sp++] = (uint16_t)x;
+        CB_LOOP
         while (sp) {
-            int y = stk[--sp];
-            st[y] = (uint16_t)b;
+            int y = stk()[--sp];
+            st()[y] = (uint16_t)b;
             if (y <= n) continue;
             uint16_t *f = flower(y);
-            for (int i = fl_len[y] - 1; i >= 0; --i) stk[sp++] = f[i];
+            CB_LOOP
+            for (int i = fl_len()[y] - 1; i >= 0; --i) stk()[sp++] = f[i];
         }
     }
     CB_HD void reverse_tail(uint16_t *f, int len) {  // reverse f[1..len)
+        CB_LOOP
         for (int a = 1, b = len - 1; a < b; ++a, --b) {
             uint16_t t = f[a];
             f[a] = f[b];
@@ -1276,9 +1368,11 @@ struct Blossom {
         }
     }
     CB_HDN int get_pr(int b, int xr) {
+        in_shared();
         uint16_t *f = flower(b);
-        int len = fl_len[b];
+        int len = fl_len()[b];
         int pr = 0;
+        CB_LOOP
         while (pr < len && f[pr] != xr) pr++;
         if (pr % 2 == 1) {
             reverse_tail(f, len);
@@ -1288,83 +1382,98 @@ struct Blossom {
     }
     CB_HD void rotate_left(uint16_t *f, int len, int k) {  // three reversals
         if (k <= 0 || k >= len) return;
+        CB_LOOP
         for (int a = 0, b = k - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
+        CB_LOOP
         for (int a = k, b = len - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
+        CB_LOOP
         for (int a = 0, b = len - 1; a < b; ++a, --b) { uint16_t t = f[a]; f[a] = f[b]; f[b] = t; }
     }
     // set_match(u, v) with an explicit stack of (u, v) pairs.
     CB_HDN void set_match(int u0, int v0) {
+        in_shared();
         int sp = 0;
-        stk[sp++] = (uint16_t)u0;
-        stk[sp++] = (uint16_t)v0;
+        stk()[sp++] = (uint16_t)u0;
+        stk()[sp++] = (uint16_t)v0;
+        CB_LOOP
         while (sp) {
-            int v = stk[--sp];
-            int u = stk[--sp];
-            match[u] = (uint16_t)gev(u, v);
+            int v = stk()[--sp];
+            int u = stk()[--sp];
+            match()[u] = (uint16_t)gev(u, v);
             if (u <= n) continue;
             int eu = geu(u, v);
             int xr = ffrom(u, eu);
             int pr = get_pr(u, xr);
             uint16_t *f = flower(u);
+            CB_LOOP
             for (int i = 0; i < pr; ++i) {
-                stk[sp++] = f[i];
-                stk[sp++] = f[i ^ 1];
+                stk()[sp++] = f[i];
+                stk()[sp++] = f[i ^ 1];
             }
-            stk[sp++] = (uint16_t)xr;
-            stk[sp++] = (uint16_t)v;
-            rotate_left(f, fl_len[u], pr);
+            stk()[sp++] = (uint16_t)xr;
+            stk()[sp++] = (uint16_t)v;
+            rotate_left(f, fl_len()[u], pr);
         }
     }
     CB_HDN void augment(int u, int v) {
+        in_shared();
+        CB_LOOP
         for (;;) {
-            int xnv = st[match[u]];
+            int xnv = st()[match()[u]];
             set_match(u, v);
             if (!xnv) return;
-            set_match(xnv, st[pa[xnv]]);
-            u = st[pa[xnv]];
+            set_match(xnv, st()[pa()[xnv]]);
+            u = st()[pa()[xnv]];
             v = xnv;
         }
     }
     CB_HDN int get_lca(int u, int v) {
+        in_shared();
+        CB_LOOP
         for (++vis_t; u || v;) {
             if (u != 0) {
-                if (vis[u] == vis_t) return u;
-                vis[u] = vis_t;
-                u = st[match[u]];
-                if (u) u = st[pa[u]];
+                if (vis()[u] == vis_t) return u;
+                vis()[u] = vis_t;
+                u = st()[match()[u]];
+                if (u) u = st()[pa()[u]];
             }
             int t = u; u = v; v = t;
         }
         return 0;
     }
     CB_HDN void add_blossom(const G &g, int u, int lca, int v) {
+        in_shared();
         int b = n + 1;
-        while (b <= n_x && st[b]) ++b;
+        CB_LOOP
+        while (b <= n_x && st()[b]) ++b;
         if (b > n_x) ++n_x;
         if (b >= NX) { broken = true; return; }
-        lab[b] = 0;
-        S[b] = 0;
-        match[b] = match[lca];
+        lab()[b] = 0;
+        S()[b] = 0;
+        match()[b] = match()[lca];
         uint16_t *f = flower(b);
         int len = 0;
         f[len++] = (uint16_t)lca;
-        for (int x = u, y; x != lca; x = st[pa[y]]) {
-            if (len + 2 > FL) { broken = true; return; }
+        CB_LOOP
+        for (int x = u, y; x != lca; x = st()[pa()[y]]) {
+            if (len + 2 > fls()) { broken = true; return; }
             f[len++] = (uint16_t)x;
-            f[len++] = (uint16_t)(y = st[match[x]]);
+            f[len++] = (uint16_t)(y = st()[match()[x]]);
             q_push(y);
         }
         reverse_tail(f, len);
-        for (int x = v, y; x != lca; x = st[pa[y]]) {
-            if (len + 2 > FL) { broken = true; return; }
+        CB_LOOP
+        for (int x = v, y; x != lca; x = st()[pa()[y]]) {
+            if (len + 2 > fls()) { broken = true; return; }
             f[len++] = (uint16_t)x;
-            f[len++] = (uint16_t)(y = st[match[x]]);
+            f[len++] = (uint16_t)(y = st()[match()[x]]);
             q_push(y);
         }
-        fl_len[b] = (uint16_t)len;
+        fl_len()[b] = (uint16_t)len;
         set_st(b, b);
         if (par) call(g, OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
         else k_blossom_clear(0, 1, b, n_x);
+        CB_LOOP
         for (int i = 0; i < len; ++i) {
             if (par) call(g, OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
             else k_merge_row(0, 1, b, f[i], n_x);
@@ -1372,40 +1481,45 @@ struct Blossom {
         set_slack(g, b);
     }
     CB_HDN void expand_blossom(const G &g, int b) {
+        in_shared();
         uint16_t *f = flower(b);
-        int len = fl_len[b];
+        int len = fl_len()[b];
+        CB_LOOP
         for (int i = 0; i < len; ++i) set_st(f[i], f[i]);
-        int xr = ffrom(b, geu(b, pa[b]));
+        int xr = ffrom(b, geu(b, pa()[b]));
         int pr = get_pr(b, xr);
+        CB_LOOP
         for (int i = 0; i < pr; i += 2) {
             int xs = f[i], xns = f[i + 1];
-            pa[xs] = (uint16_t)geu(xns, xs);
-            S[xs] = 1;
-            S[xns] = 0;
-            slack[xs] = 0;
+            pa()[xs] = (uint16_t)geu(xns, xs);
+            S()[xs] = 1;
+            S()[xns] = 0;
+            slack()[xs] = 0;
             set_slack(g, xns);
             q_push(xns);
         }
-        S[xr] = 1;
-        pa[xr] = pa[b];
+        S()[xr] = 1;
+        pa()[xr] = pa()[b];
+        CB_LOOP
         for (int i = pr + 1; i < len; ++i) {
             int xs = f[i];
-            S[xs] = -1;
+            S()[xs] = -1;
             set_slack(g, xs);
         }
-        st[b] = 0;
+        st()[b] = 0;
     }
     // e = best edge between nodes a (row) and b: endpoints (eu in a, ev in b)
     CB_HDN bool on_found_edge(const G &g, int eu, int ev) {
-        int u = st[eu], v = st[ev];
-        if (S[v] == -1) {
-            pa[v] = (uint16_t)eu;
-            S[v] = 1;
-            int nu = st[match[v]];
-            slack[v] = slack[nu] = 0;
-            S[nu] = 0;
+        in_shared();
+        int u = st()[eu], v = st()[ev];
+        if (S()[v] == -1) {
+            pa()[v] = (uint16_t)eu;
+            S()[v] = 1;
+            int nu = st()[match()[v]];
+            slack()[v] = slack()[nu] = 0;
+            S()[nu] = 0;
             q_push(nu);
-        } else if (S[v] == 0) {
+        } else if (S()[v] == 0) {
             int lca = get_lca(u, v);
             if (!lca) {
                 augment(u, v);
@@ -1417,34 +1531,40 @@ struct Blossom {
         return false;
     }
     CB_HDN bool matching(const G &g) {
+        in_shared();
         const int64_t INF = INT64_MAX / 4;
         if (par) call(g, OP_PHASE_INIT, (uint32_t)n_x);
         else k_phase_init(0, 1, n_x);
         qh = qt = 0;
+        CB_LOOP
         for (int x = 1; x <= n_x; ++x)
-            if (st[x] == x && !match[x]) {
-                pa[x] = 0;
-                S[x] = 0;
+            if (st()[x] == x && !match()[x]) {
+                pa()[x] = 0;
+                S()[x] = 0;
                 q_push(x);
             }
         if (qh == qt) return false;
+        CB_LOOP
         for (;;) {
+            CB_LOOP
             while (qh != qt) {
                 if (broken) return false;
-                int u = q[qh];
-                qh = qh + 1 == QC ? 0 : qh + 1;
-                if (S[st[u]] == 1) continue;
+                int u = q()[qh];
+                qh = qh + 1 == qcs() ? 0 : qh + 1;
+                if (S()[st()[u]] == 1) continue;
                 // neighbours of u in ascending order (adjacency bit rows; W never changes during a solve)
-                for (int k = 0; k < AW; ++k) {
-                    uint32_t bits = adjm[u * AW + k];
+                CB_LOOP
+                for (int k = 0; k < aws(); ++k) {
+                    uint32_t bits = adjm()[u * aws() + k];
+                    CB_LOOP
                     while (bits) {
                         int v = 32 * k + (int)ctz32(bits);
                         bits &= bits - 1;
-                        if (st[u] != st[v]) {
-                            if (lab[u] + lab[v] - 2 * W[u * (n + 1) + v] == 0) {
+                        if (st()[u] != st()[v]) {
+                            if (lab()[u] + lab()[v] - 2 * W()[u * ws() + v] == 0) {
                                 if (on_found_edge(g, u, v)) return true;
                             } else {
-                                update_slack(u, st[v]);
+                                update_slack(u, st()[v]);
                             }
                         }
                     }
@@ -1457,19 +1577,23 @@ struct Blossom {
             else k_lab_update(0, 1, n_x, d);
             qh = qt = 0;
             if (par) {
+                CB_LOOP
                 for (int x = (int)call(g, OP_NEXT_TIGHT, 1, (uint32_t)n_x); x <= n_x; x = (int)call(g, OP_NEXT_TIGHT, (uint32_t)(x + 1), (uint32_t)n_x))
-                    if (tight_candidate(x) && on_found_edge(g, geu(slack[x], x), gev(slack[x], x))) return true;
+                    if (tight_candidate(x) && on_found_edge(g, geu(slack()[x], x), gev(slack()[x], x))) return true;
             } else {
+                CB_LOOP
                 for (int x = 1; x <= n_x; ++x)
                     if (tight_candidate(x))
-                        if (on_found_edge(g, geu(slack[x], x), gev(slack[x], x))) return true;
+                        if (on_found_edge(g, geu(slack()[x], x), gev(slack()[x], x))) return true;
             }
+            CB_LOOP
             for (int b = n + 1; b <= n_x; ++b)
-                if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(g, b);
+                if (st()[b] == b && S()[b] == 1 && lab()[b] == 0) expand_blossom(g, b);
         }
     }
-    // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match[1..n] = partners.
+    // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match()[1..n] = partners.
     CB_HDN int solve(const G &g) {
+        in_shared();
         n_x = n;
         vis_t = 0;
         if (par) {
@@ -1481,17 +1605,20 @@ struct Blossom {
         // Greedy start on the edges that are tight under the row-maximum labels (mutual best partners), lowest indices
         // first: a valid primal-dual state that leaves only the remaining vertices to the augmentation phases.
         int cnt = 0;
+        CB_LOOP
         for (int u = 1; u <= n; ++u) {
-            if (match[u] || lab[u] <= 0) continue;
+            if (match()[u] || lab()[u] <= 0) continue;
             bool done = false;
-            for (int k = 0; k < AW && !done; ++k) {
-                uint32_t bits = adjm[u * AW + k];
+            CB_LOOP
+            for (int k = 0; k < aws() && !done; ++k) {
+                uint32_t bits = adjm()[u * aws() + k];
+                CB_LOOP
                 while (bits) {
                     int v = 32 * k + (int)ctz32(bits);
                     bits &= bits - 1;
-                    if (!match[v] && W[u * (n + 1) + v] == lab[u] && lab[v] == lab[u]) {
-                        match[u] = (uint16_t)v;
-                        match[v] = (uint16_t)u;
+                    if (!match()[v] && W()[u * ws() + v] == lab()[u] && lab()[v] == lab()[u]) {
+                        match()[u] = (uint16_t)v;
+                        match()[v] = (uint16_t)u;
                         ++cnt;
                         done = true;
                         break;
@@ -1499,10 +1626,12 @@ struct Blossom {
                 }
             }
         }
+        CB_LOOP
         while (matching(g)) ++cnt;
         return cnt;
     }
 };
+static_assert(sizeof(Blossom<HostGroup, 8>) <= Blossom<HostGroup, 8>::HDR, "Blossom header room");
 
 // ---------------------------------------------------------------------------------------------------------------
 // Stage 2 driver
@@ -1635,12 +1764,18 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     return false;
 }
 
-// Exact solve of component c by the dense blossom; every lane of the warp calls this together. Lane 0 prepares the
-// weight matrix and drives the solver, the other lanes serve its data-parallel helpers (large components only).
-// `scratch` (nullable) is fast memory the solver may use when the component fits; otherwise the scratch comes from the
-// dynamic region.
+// Scratch bytes of the solver class that handles n events: fixed layouts of 8 and 16 vertices (shared memory only), the
+// run-time sized layout beyond.
 template <class G>
-CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scratch, uint64_t scratch_bytes) {
+CB_HD uint64_t blossom_bytes(uint32_t n) {
+    if (n <= 8) return Blossom<G, 8>::bytes_needed((int)n);
+    if (n <= 16) return Blossom<G, 16>::bytes_needed((int)n);
+    return Blossom<G, 0>::bytes_needed((int)n);
+}
+
+template <class G, int CAP>
+CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
+    typedef Blossom<G, CAP> BL;
     uint32_t r = s.comp_root[c];
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
@@ -1648,23 +1783,24 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
         if (g.lane == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
         return;
     }
-    uint64_t need_bytes = Blossom<G>::bytes_needed((int)n);
     uint64_t off = 0;
     if (g.lane == 0) {
-        uint8_t *memory = (scratch && need_bytes <= scratch_bytes) ? scratch : s.alloc(need_bytes);
+        uint8_t *memory = scratch ? scratch : s.alloc(BL::bytes_needed((int)n));
         off = memory ? (uint64_t)(uintptr_t)memory : 0;
     }
     off = g.shfl64(off, 0);
     if (!off) return;
-    Blossom<G> &bl = *Blossom<G>::place((uint8_t *)(uintptr_t)off);
+    BL &bl = *BL::place((uint8_t *)(uintptr_t)off);
+    bl.in_shared();
     if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
     g.wsync();
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     // Set-up by all lanes: the weight matrix from the members' neighbour lists (global memory, one member per lane).
     // Only pairs inside the component take part; pairs seen across components are guarded by the dual check.
     const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
-    int64_t *const W = bl.W;
-    for (uint32_t k = lane; k < (n + 1) * (n + 1); k += lanes) W[k] = 0;
+    int64_t *const W = bl.W();
+    const uint32_t ws = (uint32_t)bl.ws();
+    for (uint32_t k = lane; k < (n + 1) * ws; k += lanes) W[k] = 0;
     for (uint32_t a = lane; a < n; a += lanes) s.lidx[mem[a]] = a + 1;
     g.wsync();
     int64_t big = 2;
@@ -1681,8 +1817,8 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
         for (uint32_t k = 0; k < cnt; k++) {
             if (s.root[l[k].ev] != r) continue;
             const uint32_t b = s.lidx[l[k].ev];
-            W[(a + 1) * (n + 1) + b] = big - l[k].d;  // a pair seen from both sides writes the same value twice
-            W[b * (n + 1) + (a + 1)] = big - l[k].d;
+            W[(a + 1) * ws + b] = big - l[k].d;  // a pair seen from both sides writes the same value twice
+            W[b * ws + (a + 1)] = big - l[k].d;
         }
     }
     g.wsync();
@@ -1709,21 +1845,33 @@ CB_HDN void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *sc
     if (pairs * 2 != n) {
         for (uint32_t a = lane; a < n; a += lanes) {
             s.solved[mem[a]] = 0;
-            if (!bl.match[a + 1]) request_growth(s, mem[a], -1);
+            if (!bl.match()[a + 1]) request_growth(s, mem[a], -1);
         }
         g.wsync();
         return;
     }
     for (uint32_t a = lane; a < n; a += lanes) {
         uint32_t e = mem[a];
-        int64_t need = big - bl.lab[a + 1];  // = 2 * y_a
+        int64_t need = big - bl.lab()[a + 1];  // = 2 * y_a
         s.h[e] = need;
         s.solved[e] = 1;
         s.pc[e] = mem[0];
-        s.partner[e] = (int32_t)mem[bl.match[a + 1] - 1];
+        s.partner[e] = (int32_t)mem[bl.match()[a + 1] - 1];
         if (need > s.R[e]) request_growth(s, e, need);
     }
     g.wsync();
+}
+
+// Exact solve of component c by the dense blossom; every lane of the warp calls this together. Lane 0 drives the solver,
+// the other lanes fill the weight matrix, serve the data-parallel helpers (large components only) and write back.
+// `scratch`: a slice of the shared-memory pool holding blossom_bytes(n) bytes, or nullptr (dynamic region, run-time
+// sized layout).
+template <class G>
+CB_HD void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
+    const uint32_t n = s.cnt[s.comp_root[c]];
+    if (scratch && n <= 8) solve_component_blossom_t<G, 8>(s, g, c, scratch);
+    else if (scratch && n <= 16) solve_component_blossom_t<G, 16>(s, g, c, scratch);
+    else solve_component_blossom_t<G, 0>(s, g, c, scratch);
 }
 
 template <class G>
@@ -1835,11 +1983,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                     }
                     s.uf[b] = v;
                 }
-                const uint64_t pool = s.sh_ball.H ? s.sh_tables_bytes : 0;
+                const uint64_t pool = s.sh_tables_bytes;
                 uint32_t wave = 0;
                 uint64_t top = 0;
                 for (uint32_t k = 0; k < nbig; k++) {
-                    const uint64_t need = align16(Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[s.uf[k]]]));
+                    const uint64_t need = align16(blossom_bytes<G>(s.cnt[s.comp_root[s.uf[k]]]));
                     if (need > pool) {
                         s.fillp[k] = (wave << 16) | 0xFFFFu;
                         continue;
@@ -1861,8 +2009,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                 while (k1 < nbig && (s.fillp[k1] >> 16) == wave) k1++;
                 for (uint32_t k = k0 + g.warp; k < k1; k += g.nwarps) {
                     const uint32_t off16 = s.fillp[k] & 0xFFFFu;
-                    const uint64_t need = Blossom<G>::bytes_needed((int)s.cnt[s.comp_root[s.uf[k]]]);
-                    solve_component_blossom(s, g, s.uf[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4), need);
+                    solve_component_blossom(s, g, s.uf[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
                 }
                 k0 = k1;
@@ -1893,14 +2040,18 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 // sequence src .. dst in the dynamic region. One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------
 // Writes the path src .. dst of event i's matched pair, dst being entry `at` of src's near-table row: a direct edge if
-// the entry is flagged, otherwise the chain of stored canonical predecessors. One thread.
-CB_HDN void near_path_emit(Shot &s, uint32_t i, uint32_t src, uint32_t dst, uint32_t at, bool chunked) {
+// the entry is flagged, otherwise the chain of stored canonical predecessors. One thread. Returns false when the chain
+// runs through a predecessor whose position is not stored.
+CB_HDN bool near_path_emit(Shot &s, uint32_t i, uint32_t src, uint32_t dst, uint32_t at, bool chunked) {
     const NearEntry last = *near_at(s.T, src, at);
     uint32_t len = 2;
     if (!(last.dist_flag & 0x80000000u))
-        for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; q = near_at(s.T, src, q)->node_pred >> 24) len++;
+        for (uint32_t q = last.node_pred >> 24; q != NEAR_PRED_SRC; q = near_at(s.T, src, q)->node_pred >> 24) {
+            if (q == NEAR_PRED_FAR) return false;  // predecessor position not stored: the caller searches
+            len++;
+        }
     uint32_t *out = (uint32_t *)(chunked ? s.alloc_small(uint64_t{len} * 4) : s.alloc(uint64_t{len} * 4));
-    if (!out) return;
+    if (!out) return true;  // alloc flagged the overflow
     out[0] = src;
     out[len - 1] = dst;
     uint32_t k = len - 2;
@@ -1912,6 +2063,7 @@ CB_HDN void near_path_emit(Shot &s, uint32_t i, uint32_t src, uint32_t dst, uint
         }
     s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
     s.path_len[i] = len;
+    return true;
 }
 
 // Path of a matched pair from the near table of `src`: find `dst` in the row, then follow the stored canonical
@@ -1934,9 +2086,10 @@ CB_HDN bool extract_path_near(Shot &s, const G &g, uint32_t i, uint32_t src, uin
         if (g.ballot(pad || d > d_total)) return false;
     }
     if (at == NO_INDEX) return false;
-    if (lane == 0) near_path_emit(s, i, src, dst, at, true);
+    uint32_t ok = 0;
+    if (lane == 0) ok = near_path_emit(s, i, src, dst, at, true) ? 1 : 0;
     g.wsync();
-    return true;
+    return g.shfl32(ok, 0) != 0;
 }
 
 template <class G>
@@ -2066,10 +2219,8 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
         const NbEntry *l = nb_list(s, i);
         for (uint32_t k = 0; k < s.nb_cnt[i]; k++)
             if (l[k].ev == (uint32_t)j) {
-                if (l[k].pos != NO_INDEX) {
+                if (l[k].pos != NO_INDEX && near_path_emit(s, i, s.event_node(i), s.event_node((uint32_t)j), l[k].pos, false))
                     wsum += (uint64_t)l[k].d;
-                    near_path_emit(s, i, s.event_node(i), s.event_node((uint32_t)j), l[k].pos, false);
-                }
                 break;
             }
     }

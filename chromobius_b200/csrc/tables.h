@@ -42,7 +42,8 @@ struct AdjEntry {
 // canonical shortest-path predecessor. A ball query that stays inside the table is one or two coalesced row reads and a
 // ballot against the shot's event bits instead of a Dijkstra search; queries that leave it fall back to the search.
 //   node_pred : bits 0-23 node id, bits 24-31 position (within the same row) of the canonical predecessor on the
-//               shortest path from the row's node, NEAR_PRED_SRC when the predecessor is the row's node itself.
+//               shortest path from the row's node, NEAR_PRED_SRC when the predecessor is the row's node itself,
+//               NEAR_PRED_FAR when its position does not fit 8 bits (paths through it are searched instead).
 //               Canonical = the smallest-id neighbour w of the entry with dist(w) + wt(w, entry) == dist(entry).
 //   dist_flag : bits 0-30 exact distance, bit 31 set when the row's node and the entry are joined by a direct edge of
 //               exactly that weight. Rows shorter than the stride are padded with dist_flag == NEAR_PAD.
@@ -54,7 +55,8 @@ struct NearEntry {
 };
 constexpr uint32_t NEAR_PAD = 0xFFFFFFFFu;
 constexpr uint32_t NEAR_PRED_SRC = 0xFFu;
-constexpr uint32_t NEAR_MAX_STRIDE = 224;  // predecessor positions are 8 bits, 0xFF is reserved
+constexpr uint32_t NEAR_PRED_FAR = 0xFEu;
+constexpr uint32_t NEAR_MAX_STRIDE = 512;
 
 // Views used by the per-shot code (host build and device build alike).
 struct TablesView {

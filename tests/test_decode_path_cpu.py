@@ -35,7 +35,7 @@ def test_device_logic_matches_oracle(built, name, shots):
     assert int((obs != o_obs).sum()) <= max(1, shots // 300)
 
 
-@pytest.mark.parametrize('stride', [0, 32, 64])
+@pytest.mark.parametrize('stride', [0, 32, 64, 512])
 @pytest.mark.parametrize('name,shots', [('midout_color_code_d5_r10_p1000', 600), ('color2surface_d7_phenom_r7_p100', 200),
                                         ('rep_code_rg_d9_transit_p10', 400)])
 def test_near_table_sizes_give_identical_results(built, monkeypatch, name, shots, stride):
