@@ -963,7 +963,10 @@ CB_HDN void explore_first_near(Shot &s, const G &g) {
 // lowest index), so the matching and the duals do not depend on the number of lanes. Small components run on the
 // master alone (`par == false`), and so does the host build (one lane).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BLOSSOM_PAR_MIN = 12;  // components with at least this many events use the warp helpers
+#ifndef CB_BLOSSOM_PAR_MIN
+#define CB_BLOSSOM_PAR_MIN 33
+#endif
+constexpr int BLOSSOM_PAR_MIN = CB_BLOSSOM_PAR_MIN;  // components with at least this many events use the warp helpers
 
 template <class G, int CAP = 0>
 struct Blossom {
@@ -1075,7 +1078,7 @@ struct Blossom {
         AW = (n + 32) / 32;
         wide = !CAP && n > (int)NARROW_COMPONENT;
         broken = false;
-        par = lanes > 1 && n >= BLOSSOM_PAR_MIN;
+        par = !CAP && lanes > 1 && n >= BLOSSOM_PAR_MIN;  // the fixed layouts are fastest on one lane
         n_x = n;
         if (CAP) return;
         uint8_t *p = mem + align16(sizeof(Blossom));
@@ -1764,12 +1767,13 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     return false;
 }
 
-// Scratch bytes of the solver class that handles n events: fixed layouts of 8 and 16 vertices (shared memory only), the
+// Scratch bytes of the solver class that handles n events: fixed layouts of 8, 16 and 32 vertices (shared memory only), the
 // run-time sized layout beyond.
 template <class G>
 CB_HD uint64_t blossom_bytes(uint32_t n) {
     if (n <= 8) return Blossom<G, 8>::bytes_needed((int)n);
     if (n <= 16) return Blossom<G, 16>::bytes_needed((int)n);
+    if (n <= 32) return Blossom<G, 32>::bytes_needed((int)n);
     return Blossom<G, 0>::bytes_needed((int)n);
 }
 
@@ -1871,6 +1875,7 @@ CB_HD void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scr
     const uint32_t n = s.cnt[s.comp_root[c]];
     if (scratch && n <= 8) solve_component_blossom_t<G, 8>(s, g, c, scratch);
     else if (scratch && n <= 16) solve_component_blossom_t<G, 16>(s, g, c, scratch);
+    else if (scratch && n <= 32) solve_component_blossom_t<G, 32>(s, g, c, scratch);
     else solve_component_blossom_t<G, 0>(s, g, c, scratch);
 }
 
@@ -1971,23 +1976,25 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         // slice, and what does not fit next to the others waits for the next wave (components beyond the whole pool use
         // the dynamic region). s.uf holds the components, s.fillp their (wave << 16 | offset / 16); both are free here.
         if (nbig) {
-            if (g.tid == 0) {
-                for (uint32_t a = 1; a < nbig; a++) {  // insertion sort: (size descending, root ascending)
-                    const uint32_t v = s.uf[a], vn = s.cnt[s.comp_root[v]], vr = s.comp_root[v];
-                    uint32_t b = a;
-                    while (b > 0) {
-                        const uint32_t u = s.uf[b - 1], un = s.cnt[s.comp_root[u]];
-                        if (un > vn || (un == vn && s.comp_root[u] < vr)) break;
-                        s.uf[b] = u;
-                        b--;
-                    }
-                    s.uf[b] = v;
+            // order: (size descending, root ascending), by counting predecessors -- one thread per component.
+            // s.path_off (unused until the path phase) receives the ordered list, s.fillp the sizes.
+            for (uint32_t k = (uint32_t)g.tid; k < nbig; k += (uint32_t)g.n) {
+                const uint32_t v = s.uf[k], vr = s.comp_root[v], vn = s.cnt[vr];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < nbig; j++) {
+                    const uint32_t ur = s.comp_root[s.uf[j]], un = s.cnt[ur];
+                    rank += (un > vn || (un == vn && ur < vr)) ? 1u : 0u;
                 }
+                s.path_off[rank] = v;
+                s.fillp[rank] = vn;
+            }
+            g.sync();
+            if (g.tid == 0) {
                 const uint64_t pool = s.sh_tables_bytes;
                 uint32_t wave = 0;
                 uint64_t top = 0;
                 for (uint32_t k = 0; k < nbig; k++) {
-                    const uint64_t need = align16(blossom_bytes<G>(s.cnt[s.comp_root[s.uf[k]]]));
+                    const uint64_t need = align16(blossom_bytes<G>(s.fillp[k]));
                     if (need > pool) {
                         s.fillp[k] = (wave << 16) | 0xFFFFu;
                         continue;
@@ -2009,7 +2016,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                 while (k1 < nbig && (s.fillp[k1] >> 16) == wave) k1++;
                 for (uint32_t k = k0 + g.warp; k < k1; k += g.nwarps) {
                     const uint32_t off16 = s.fillp[k] & 0xFFFFu;
-                    solve_component_blossom(s, g, s.uf[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
+                    solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
                 }
                 k0 = k1;

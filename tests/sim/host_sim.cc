@@ -76,7 +76,8 @@ int cbsim_decode(void *h, const uint8_t *dets, uint64_t num_shots, uint64_t stri
     p.edge_dump_len = num_edge_ints;
     p.cfg.sh_ht_log2 = sh_ht_log2;
     p.cfg.sh_found = 8;
-    p.cfg.sh_pool = 12u << 10;  // room for one fixed-layout blossom of either class; larger components use the run-time layout
+    p.cfg.sh_pool = 20u << 10;  // room for one fixed-layout blossom of any class; larger components use the run-time layout
+    if (const char *env = getenv("CBSIM_POOL_KB")) p.cfg.sh_pool = (uint32_t)strtoul(env, nullptr, 10) << 10;
     p.cfg.ht_log2 = ht_log2;
     p.cfg.found_cap = 256;
     p.cfg.max_events = 2 * s->tables.num_dets + 2;

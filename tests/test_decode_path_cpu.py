@@ -59,6 +59,18 @@ def test_near_table_sizes_give_identical_results(built, monkeypatch, name, shots
         assert (a[4] == b[4]).all(), 'matched edge lists must not depend on the near-table size'
 
 
+@pytest.mark.parametrize('pool_kb', [0, 3, 8])
+def test_blossom_layout_classes_agree(built, monkeypatch, pool_kb):
+    """Fixed-layout (8 / 16 / 32 vertices, shared pool) and run-time sized blossoms give the same matching and duals."""
+    text = read_dem('color2surface_d7_phenom_r7_p100')   # p = 1 %: dense syndromes, blossoms of every size class
+    dets, _ = NumpyDemSampler(text).sample(250, seed=9)
+    full = SimDecoder(text).decode(dets)
+    monkeypatch.setenv('CBSIM_POOL_KB', str(pool_kb))
+    other = SimDecoder(text).decode(dets)
+    assert (full[2] == 0).all() and (other[2] == 0).all()
+    assert (other[0] == full[0]).all() and (other[1] == full[1]).all() and (other[3] == full[3]).all()
+
+
 def test_device_logic_survives_tiny_scratch(built):
     """Scratch overflow is reported per shot (status 1), never silently wrong."""
     text = read_dem('midout_color_code_d5_r10_p1000')
