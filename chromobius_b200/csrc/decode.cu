@@ -298,7 +298,13 @@ void upload_tables(cb200_decoder *d) {
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, d->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, d->device);
-    if (max_persist > 0 && max_window > 0 && total > 0) {
+    // Only the head of the allocation is worth pinning: the first chunks of the near-table rows (the layout is chunk-major
+    // and the near table comes first). The per-shot scratch of the shots in flight needs the rest of the L2.
+    size_t hot = total;
+    if (h.near_stride) hot = std::min<size_t>(total, (size_t)h.num_dets * 2 * 32 * sizeof(NearEntry) * 2);
+    if (const char *env = getenv("CB200_L2_WINDOW_MB")) hot = std::min<size_t>(total, (size_t)strtoul(env, nullptr, 10) << 20);
+    if (max_persist > 0 && max_window > 0 && hot > 0) {
+        total = hot;
         size_t want = std::min<size_t>(total, (size_t)max_persist);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             cudaStreamAttrValue attr{};

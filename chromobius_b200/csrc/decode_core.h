@@ -258,9 +258,9 @@ CB_HD void bind_ball_tables(BallTables &t, uint8_t *p, uint32_t log2, uint32_t f
 // Per-event arrays (all sized max_events), see struct Shot.
 CB_HD uint64_t event_bytes(const ScratchConfig &c) {
     uint64_t m = c.max_events;
-    // evdet(u32) R(i64) h(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) + 10 x u32 + 5 x u8
+    // evdet(u32) R(i64) h(i64) nb_off nb_cnt grow_ev(u32) grow_to(i64) partner(i32) + 11 x u32 + 5 x u8
     return align16(m * 4) + align16(m * 8) * 2 + align16(m * 4) * 2 + align16(m * 4) + align16(m * 8) + align16(m * 4) +
-           align16(m * 4) * 10 + align16(m) * 5;
+           align16(m * 4) * 11 + align16(m) * 5;
 }
 CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets, uint32_t nwarps) {
     uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
@@ -296,7 +296,7 @@ struct Shot {
     uint32_t *grow_ev;
     int64_t *grow_to;
     int32_t *partner;
-    uint32_t *uf, *root, *cnt, *start, *fillp, *members, *lidx, *comp_root, *path_off, *path_len;
+    uint32_t *uf, *root, *cnt, *start, *fillp, *members, *lidx, *comp_root, *path_off, *path_len, *blist;
     uint32_t *pc;          // solved events: smallest member of the component they were last solved in
     uint8_t *solved;       // the event holds a partner and a dual from a perfect solve of its component
     uint8_t *regrown;      // the ball grew since the component was last looked at
@@ -374,7 +374,7 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.grow_ev = (uint32_t *)q; q += align16(m * 4);
     s.grow_to = (int64_t *)q; q += align16(m * 8);
     s.partner = (int32_t *)q; q += align16(m * 4);
-    uint32_t **arrs[] = {&s.uf, &s.root, &s.cnt, &s.start, &s.fillp, &s.members, &s.lidx, &s.comp_root, &s.path_off, &s.pc};
+    uint32_t **arrs[] = {&s.uf, &s.root, &s.cnt, &s.start, &s.fillp, &s.members, &s.lidx, &s.comp_root, &s.path_off, &s.pc, &s.blist};
     for (auto a : arrs) { *a = (uint32_t *)q; q += align16(m * 4); }
     s.path_len = s.fillp;  // fillp is dead once the matcher has finished; path_len is only used afterwards
     s.solved = q; q += align16(m);
@@ -1891,12 +1891,17 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         s.pc[i] = NO_INDEX;
         s.nb_cnt[i] = 0;
         s.used_flag[i] = 0;
+        s.uf[i] = i;
+        s.comp_dirty[i] = 0;
+        s.cnt[i] = 0;
     }
+    if (g.tid == 0) s.hdr->ncomp = 0;
     g.sync();
     explore_first_near(s, g);
     for (uint32_t i = g.warp; i < M; i += g.nwarps)
         if (s.nb_cnt[i] == 0) explore_event(s, g, i, -1, 0);
     uint32_t round = 0;
+    uint32_t *const act = s.lidx;  // events of this round's dirty components (lidx is only used inside the blossom solves)
     while (true) {
         g.sync();
         pt.lap(round == 0 ? 1 : 4);
@@ -1906,25 +1911,29 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             g.sync();
             return round;
         }
-        for (uint32_t i = g.tid; i < M; i += g.n) {
-            s.uf[i] = i;
-            s.comp_dirty[i] = 0;
-            s.cnt[i] = 0;
+        // The union-find persists across rounds: every union ever made stays valid (a solved component stays whole, an
+        // unsolved one re-joins everything it has seen), so a round only adds unions. What the previous round's dirty
+        // components used is reset here; everything else below touches all events in three passes only.
+        const uint32_t prev_ncomp = s.hdr->ncomp;
+        for (uint32_t c = g.tid; c < prev_ncomp; c += g.n) {
+            const uint32_t r = s.comp_root[c];
+            s.cnt[r] = 0;
+            s.comp_dirty[r] = 0;
         }
+        g.sync();
         if (g.tid == 0) {
             s.hdr->ncomp = 0;
             s.hdr->mem_top = 0;
             s.hdr->ngrow = 0;
             s.hdr->nbig = 0;
-            s.hdr->nhuge = 0;
+            s.hdr->nhuge = 0;  // number of active events
         }
         g.sync();
-        // Lazy merging: a solved component stays whole; two events are joined when either has no dual yet or their duals
-        // overlap (h_i + h_j > 2 d). A violated pair inside one solved component is either an old blossom-internal edge or a
-        // pair first seen after the solve -- only a ball that grew since can show the latter, which marks it stale.
+        // Lazy merging: two events are joined when either has no dual yet or their duals overlap (h_i + h_j > 2 d).
+        // A violated pair inside one solved component is either an old blossom-internal edge or a pair first seen after
+        // the solve -- only a ball that grew since can show the latter, which marks it stale.
         for (uint32_t i = g.tid; i < M; i += g.n) {
             const bool si = s.solved[i] != 0;
-            if (si) uf_union(s.uf, i, s.pc[i]);
             const NbEntry *l = nb_list(s, i);
             for (uint32_t k = 0; k < s.nb_cnt[i]; k++) {
                 uint32_t j = l[k].ev;
@@ -1938,6 +1947,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         for (uint32_t i = g.tid; i < M; i += g.n) {
             uint32_t r = uf_find(s.uf, i);
             s.root[i] = r;
+            s.uf[i] = r;  // path compression (concurrent finds still see an ancestor)
             s.regrown[i] = 0;
             // a component is (re)solved when a member has no dual, when it joins events of different solved components,
             // or when a solved component went stale
@@ -1945,44 +1955,49 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         }
         g.sync();
         for (uint32_t i = g.tid; i < M; i += g.n)
-            if (s.comp_dirty[s.root[i]]) cb_atomic_add(&s.cnt[s.root[i]], 1);
+            if (s.comp_dirty[s.root[i]]) {
+                cb_atomic_add(&s.cnt[s.root[i]], 1);
+                act[cb_atomic_add(&s.hdr->nhuge, 1)] = i;
+            }
         g.sync();
-        for (uint32_t i = g.tid; i < M; i += g.n)
-            if (s.root[i] == i && s.comp_dirty[i]) {
+        const uint32_t nact = s.hdr->nhuge;
+        for (uint32_t k = g.tid; k < nact; k += g.n) {
+            const uint32_t i = act[k];
+            if (s.root[i] == i) {
                 uint32_t slot = cb_atomic_add(&s.hdr->ncomp, 1);
                 s.comp_root[slot] = i;
                 s.start[i] = cb_atomic_add(&s.hdr->mem_top, s.cnt[i]);
                 s.fillp[i] = 0;
             }
+        }
         g.sync();
-        for (uint32_t i = g.tid; i < M; i += g.n) {
-            uint32_t r = s.root[i];
-            if (s.comp_dirty[r]) {
-                uint32_t p = cb_atomic_add(&s.fillp[r], 1);
-                s.members[s.start[r] + p] = i;
-                if (s.solved[i]) s.stale[s.pc[i]] = 0;
-            }
+        for (uint32_t k = g.tid; k < nact; k += g.n) {
+            const uint32_t i = act[k];
+            const uint32_t r = s.root[i];
+            uint32_t p = cb_atomic_add(&s.fillp[r], 1);
+            s.members[s.start[r] + p] = i;
+            if (s.solved[i]) s.stale[s.pc[i]] = 0;
         }
         g.sync();
         const uint32_t ncomp = s.hdr->ncomp;
         pt.lap(2);
-        // small components: one thread each; the rest is queued for the blossom (s.uf is free until the next round)
+        // small components: one thread each; the rest is queued for the blossom
         for (uint32_t c = g.tid; c < ncomp; c += g.n)
-            if (!solve_component_small(s, c)) s.uf[cb_atomic_add(&s.hdr->nbig, 1)] = c;
+            if (!solve_component_small(s, c)) s.blist[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
         pt.lap(8);
         const uint32_t nbig = s.hdr->nbig;
         // Blossom components share the group's shared-memory table space as one pool: largest first, each gets its own
         // slice, and what does not fit next to the others waits for the next wave (components beyond the whole pool use
-        // the dynamic region). s.uf holds the components, s.fillp their (wave << 16 | offset / 16); both are free here.
+        // the dynamic region). s.blist holds the components, s.fillp their (wave << 16 | offset / 16).
         if (nbig) {
             // order: (size descending, root ascending), by counting predecessors -- one thread per component.
             // s.path_off (unused until the path phase) receives the ordered list, s.fillp the sizes.
             for (uint32_t k = (uint32_t)g.tid; k < nbig; k += (uint32_t)g.n) {
-                const uint32_t v = s.uf[k], vr = s.comp_root[v], vn = s.cnt[vr];
+                const uint32_t v = s.blist[k], vr = s.comp_root[v], vn = s.cnt[vr];
                 uint32_t rank = 0;
                 for (uint32_t j = 0; j < nbig; j++) {
-                    const uint32_t ur = s.comp_root[s.uf[j]], un = s.cnt[ur];
+                    const uint32_t ur = s.comp_root[s.blist[j]], un = s.cnt[ur];
                     rank += (un > vn || (un == vn && ur < vr)) ? 1u : 0u;
                 }
                 s.path_off[rank] = v;
