@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict_
 #define CB_MIN_BLOCKS_256 3
 #endif
 template <int GROUP>
-__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? CB_MIN_BLOCKS_256 : 6))
+__global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? CB_MIN_BLOCKS_256 : (GROUP == 192 ? 4 : 6)))
     k_decode(DecodeParams p, uint32_t num_groups, uint32_t smem_per_group) {
     uint32_t group, gib;
     DevGroup<GROUP> g;
@@ -380,7 +380,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     Plan pl{};
     uint32_t group = d->tune_group;
     if (group == 0) group = mean_det_events >= 200 ? 256 : (mean_det_events >= 8 ? 128 : 32);
-    if (group != 32 && group != 128 && group != 256 && group != 512) group = 32;
+    if (group != 32 && group != 128 && group != 192 && group != 256 && group != 512) group = 32;
     pl.group = group;
     uint32_t full = 4;
     while ((1u << full) < 2 * std::max<uint32_t>(d->dview.num_nodes, 8)) full++;
@@ -404,6 +404,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
         switch (group) {
             case 32: return blocks_per_sm<32>(smem) * (WARP_MODE_BLOCK / 32);
             case 128: return blocks_per_sm<128>(smem);
+            case 192: return blocks_per_sm<192>(smem);
             case 256: return blocks_per_sm<256>(smem);
             default: return blocks_per_sm<512>(smem);
         }
@@ -434,6 +435,7 @@ void ensure_arena(cb200_decoder *d, const Plan &pl, DecodeParams &p, uint64_t &l
         p.arena = a.buf.ptr;
         if (pl.group == 32) launch_init<32>(p, pl.groups, d->stream);
         else if (pl.group == 128) launch_init<128>(p, pl.groups, d->stream);
+        else if (pl.group == 192) launch_init<192>(p, pl.groups, d->stream);
         else if (pl.group == 256) launch_init<256>(p, pl.groups, d->stream);
         else launch_init<512>(p, pl.groups, d->stream);
         CUDA_CHECK(cudaGetLastError());
@@ -544,6 +546,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         }
         if (pl.group == 32) launch_decode<32>(p, pl.groups, pl.smem_per_group, s);
         else if (pl.group == 128) launch_decode<128>(p, pl.groups, pl.smem_per_group, s);
+        else if (pl.group == 192) launch_decode<192>(p, pl.groups, pl.smem_per_group, s);
         else if (pl.group == 256) launch_decode<256>(p, pl.groups, pl.smem_per_group, s);
         else launch_decode<512>(p, pl.groups, pl.smem_per_group, s);
         CUDA_CHECK(cudaGetLastError());
@@ -709,8 +712,9 @@ char *cb200_describe(const cb200_decoder *d) {
 void cb200_free_string(char *s) { free(s); }
 
 int cb200_set_tuning(cb200_decoder *d, uint32_t group_threads, uint32_t ht_log2) {
-    if (group_threads != 0 && group_threads != 32 && group_threads != 128 && group_threads != 256 && group_threads != 512) {
-        g_error = "group_threads must be 0, 32, 128, 256 or 512";
+    if (group_threads != 0 && group_threads != 32 && group_threads != 128 && group_threads != 192 && group_threads != 256 &&
+        group_threads != 512) {
+        g_error = "group_threads must be 0, 32, 128, 192, 256 or 512";
         return CB200_ERR_INVALID_ARGUMENT;
     }
     if (ht_log2 != 0 && (ht_log2 < 4 || ht_log2 > 24)) {

@@ -1101,6 +1101,7 @@ struct Blossom {
     }
     CB_HD int64_t &w(int u, int v) { return W()[u * ws() + v]; }
     CB_HD bool is_wide() const { return !CAP && wide; }
+    CB_HD bool is_par() const { return !CAP && par; }  // the fixed layouts always run on one lane
     CB_HD int geu(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2] : ge()[(a * nxs() + b) * 2]; }
     CB_HD int gev(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2 + 1] : ge()[(a * nxs() + b) * 2 + 1]; }
     CB_HD bool has(int a, int b) const { return geu(a, b) != 0; }
@@ -1311,7 +1312,7 @@ struct Blossom {
         }
     }
     CB_HD void release_workers(const G &g) {
-        if (par) {
+        if (is_par()) {
             cmd()[0] = OP_EXIT;
             g.wsync();
         }
@@ -1323,7 +1324,7 @@ struct Blossom {
     }
     CB_HDN void set_slack(const G &g, int x) {
         in_shared();
-        uint64_t best = par ? call(g, OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
+        uint64_t best = is_par() ? call(g, OP_SET_SLACK, (uint32_t)x) : k_set_slack(0, 1, x);
         slack()[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
     }
     CB_HD void q_put(int v) {
@@ -1474,11 +1475,11 @@ struct Blossom {
         }
         fl_len()[b] = (uint16_t)len;
         set_st(b, b);
-        if (par) call(g, OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
+        if (is_par()) call(g, OP_BLOSSOM_CLEAR, (uint32_t)b, (uint32_t)n_x);
         else k_blossom_clear(0, 1, b, n_x);
         CB_LOOP
         for (int i = 0; i < len; ++i) {
-            if (par) call(g, OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
+            if (is_par()) call(g, OP_MERGE_ROW, (uint32_t)b, (uint32_t)f[i], (uint32_t)n_x);
             else k_merge_row(0, 1, b, f[i], n_x);
         }
         set_slack(g, b);
@@ -1536,7 +1537,7 @@ struct Blossom {
     CB_HDN bool matching(const G &g) {
         in_shared();
         const int64_t INF = INT64_MAX / 4;
-        if (par) call(g, OP_PHASE_INIT, (uint32_t)n_x);
+        if (is_par()) call(g, OP_PHASE_INIT, (uint32_t)n_x);
         else k_phase_init(0, 1, n_x);
         qh = qt = 0;
         CB_LOOP
@@ -1574,12 +1575,12 @@ struct Blossom {
                 }
             }
             if (broken) return false;
-            int64_t d = (int64_t)(par ? call(g, OP_DUAL_MIN, (uint32_t)n_x) : k_dual_min(0, 1, n_x));
+            int64_t d = (int64_t)(is_par() ? call(g, OP_DUAL_MIN, (uint32_t)n_x) : k_dual_min(0, 1, n_x));
             if (d >= INF) return false;
-            if (par) call(g, OP_LAB_UPDATE, (uint32_t)n_x, (uint32_t)((uint64_t)d & 0xFFFFFFFFu), (uint32_t)((uint64_t)d >> 32));
+            if (is_par()) call(g, OP_LAB_UPDATE, (uint32_t)n_x, (uint32_t)((uint64_t)d & 0xFFFFFFFFu), (uint32_t)((uint64_t)d >> 32));
             else k_lab_update(0, 1, n_x, d);
             qh = qt = 0;
-            if (par) {
+            if (is_par()) {
                 CB_LOOP
                 for (int x = (int)call(g, OP_NEXT_TIGHT, 1, (uint32_t)n_x); x <= n_x; x = (int)call(g, OP_NEXT_TIGHT, (uint32_t)(x + 1), (uint32_t)n_x))
                     if (tight_candidate(x) && on_found_edge(g, geu(slack()[x], x), gev(slack()[x], x))) return true;
@@ -1599,7 +1600,7 @@ struct Blossom {
         in_shared();
         n_x = n;
         vis_t = 0;
-        if (par) {
+        if (is_par()) {
             call(g, OP_INIT);
         } else {
             k_init(0, 1);
@@ -1777,33 +1778,12 @@ CB_HD uint64_t blossom_bytes(uint32_t n) {
     return Blossom<G, 0>::bytes_needed((int)n);
 }
 
-template <class G, int CAP>
-CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
-    typedef Blossom<G, CAP> BL;
-    uint32_t r = s.comp_root[c];
-    uint32_t n = s.cnt[r];
-    uint32_t *mem = s.members + s.start[r];
-    if (n > MAX_COMPONENT) {
-        if (g.lane == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
-        return;
-    }
-    uint64_t off = 0;
-    if (g.lane == 0) {
-        uint8_t *memory = scratch ? scratch : s.alloc(BL::bytes_needed((int)n));
-        off = memory ? (uint64_t)(uintptr_t)memory : 0;
-    }
-    off = g.shfl64(off, 0);
-    if (!off) return;
-    BL &bl = *BL::place((uint8_t *)(uintptr_t)off);
-    bl.in_shared();
-    if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
-    g.wsync();
-    const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
-    // Set-up by all lanes: the weight matrix from the members' neighbour lists (global memory, one member per lane).
-    // Only pairs inside the component take part; pairs seen across components are guarded by the dual check.
+// Set-up shared by every solver class, all lanes: clears the weight matrix W (row stride ws) and fills it from the
+// members' neighbour lists (global memory, one member per lane). Only pairs inside the component take part; pairs seen
+// across components are guarded by the dual check. Returns `big` (weights are big - distance).
+template <class G>
+CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n, const uint32_t *mem, int64_t *W, uint32_t ws) {
     const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
-    int64_t *const W = bl.W();
-    const uint32_t ws = (uint32_t)bl.ws();
     for (uint32_t k = lane; k < (n + 1) * ws; k += lanes) W[k] = 0;
     for (uint32_t a = lane; a < n; a += lanes) s.lidx[mem[a]] = a + 1;
     g.wsync();
@@ -1826,8 +1806,59 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
         }
     }
     g.wsync();
+    return big;
+}
+
+// Write-back shared by every solver class, all lanes, one member each.
+template <class G>
+CB_HDN void blossom_write_back(Shot &s, const G &g, uint32_t n, const uint32_t *mem, uint32_t pairs, int64_t big,
+                               const uint16_t *match, const int64_t *lab) {
+    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    if (pairs * 2 != n) {
+        for (uint32_t a = lane; a < n; a += lanes) {
+            s.solved[mem[a]] = 0;
+            if (!match[a + 1]) request_growth(s, mem[a], -1);
+        }
+        g.wsync();
+        return;
+    }
+    for (uint32_t a = lane; a < n; a += lanes) {
+        uint32_t e = mem[a];
+        int64_t need = big - lab[a + 1];  // = 2 * y_a
+        s.h[e] = need;
+        s.solved[e] = 1;
+        s.pc[e] = mem[0];
+        s.partner[e] = (int32_t)mem[match[a + 1] - 1];
+        if (need > s.R[e]) request_growth(s, e, need);
+    }
+    g.wsync();
+}
+
+template <class G, int CAP>
+CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
+    typedef Blossom<G, CAP> BL;
+    uint32_t r = s.comp_root[c];
+    uint32_t n = s.cnt[r];
+    uint32_t *mem = s.members + s.start[r];
+    if (n > MAX_COMPONENT) {
+        if (g.lane == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
+        return;
+    }
+    uint64_t off = 0;
+    if (g.lane == 0) {
+        uint8_t *memory = scratch ? scratch : s.alloc(BL::bytes_needed((int)n));
+        off = memory ? (uint64_t)(uintptr_t)memory : 0;
+    }
+    off = g.shfl64(off, 0);
+    if (!off) return;
+    BL &bl = *BL::place((uint8_t *)(uintptr_t)off);
+    bl.in_shared();
+    if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
+    g.wsync();
+    const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
+    const int64_t big = blossom_fill_weights(s, g, r, n, mem, bl.W(), (uint32_t)bl.ws());
     uint32_t pairs = 0;
-    if (lane == 0) {
+    if (g.lane == 0) {
         pairs = (uint32_t)bl.solve(g);
         bl.release_workers(g);
         if (s.prof) {
@@ -1836,34 +1867,16 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
             cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
         }
         if (bl.broken) pairs = NO_INDEX;
-    } else if (bl.par) {
+    } else if (bl.is_par()) {
         bl.worker_loop(g);
     }
     g.wsync();
     pairs = g.shfl32(pairs, 0);
     if (pairs == NO_INDEX) {
-        if (lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
-    // Write-back by all lanes, one member each.
-    if (pairs * 2 != n) {
-        for (uint32_t a = lane; a < n; a += lanes) {
-            s.solved[mem[a]] = 0;
-            if (!bl.match()[a + 1]) request_growth(s, mem[a], -1);
-        }
-        g.wsync();
-        return;
-    }
-    for (uint32_t a = lane; a < n; a += lanes) {
-        uint32_t e = mem[a];
-        int64_t need = big - bl.lab()[a + 1];  // = 2 * y_a
-        s.h[e] = need;
-        s.solved[e] = 1;
-        s.pc[e] = mem[0];
-        s.partner[e] = (int32_t)mem[bl.match()[a + 1] - 1];
-        if (need > s.R[e]) request_growth(s, e, need);
-    }
-    g.wsync();
+    blossom_write_back(s, g, n, mem, pairs, big, bl.match(), bl.lab());
 }
 
 // Exact solve of component c by the dense blossom; every lane of the warp calls this together. Lane 0 drives the solver,

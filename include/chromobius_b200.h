@@ -95,7 +95,7 @@ int cb200_decode_batch(cb200_decoder *dec, const uint8_t *dets, uint64_t num_sho
 int cb200_decode_shot_edges(cb200_decoder *dec, const uint8_t *dets_row, int64_t *edges_out, uint64_t edges_cap,
                             uint64_t *num_edge_ints, uint64_t *obs_mask_out, int64_t *weight_int_out);
 
-/* Tuning knobs (0 keeps the automatic choice): threads per shot in the decode kernel (32, 128, 256 or 512) and the
+/* Tuning knobs (0 keeps the automatic choice): threads per shot in the decode kernel (32, 128, 192, 256 or 512) and the
  * log2 size of the per-warp shared-memory ball table. */
 int cb200_set_tuning(cb200_decoder *dec, uint32_t group_threads, uint32_t ht_log2);
 /* Caps the number of shots in flight per SM (0 = as many as fit). Fewer shots in flight keep the per-shot scratch
