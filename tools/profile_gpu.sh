@@ -2,8 +2,8 @@
 # Runs on the GPU box (under gpurun): plain bench run, then the ncu launch list and one full capture of the decode kernel.
 set -u
 mkdir -p gpurun_out
-SHOTS=${1:-2048}
-CMD="python bench.py --steps 1 --warmup 1 --shots $SHOTS --e2e-shots 1024 --skip-cpu"
+SHOTS=${1:-65536}
+CMD="python bench.py --steps 2 --warmup 1 --shots $SHOTS --e2e-shots 1024 --skip-cpu"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
