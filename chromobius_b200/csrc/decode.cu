@@ -656,7 +656,7 @@ int cb200_compile(const char *dem_text, int device, cb200_decoder **out) {
     int rc = guarded([&]() {
         if (!dem_text) throw std::invalid_argument("dem_text must not be null");
         d = new cb200_decoder();
-        d->host = compile_tables(FlatDem::parse(dem_text));
+        d->host = compile_tables_cached(dem_text);
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)

@@ -1021,6 +1021,147 @@ HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
     return t;
 }
 
+// =================================================================================================
+// On-disk cache of compiled tables.
+// File: magic, version, key, then every field in declaration order; vectors as (u64 count, raw elements).
+// =================================================================================================
+namespace {
+constexpr uint64_t CACHE_MAGIC = 0x3030324253454c42ull;  // "BLESB200"
+constexpr uint64_t CACHE_VERSION = 3;
+
+struct Writer {
+    FILE *f;
+    bool ok = true;
+    void raw(const void *p, size_t n) { ok = ok && (n == 0 || fwrite(p, 1, n, f) == n); }
+    template <class T> void pod(const T &v) { raw(&v, sizeof(T)); }
+    template <class T> void vec(const std::vector<T> &v) {
+        pod<uint64_t>(v.size());
+        raw(v.data(), v.size() * sizeof(T));
+    }
+};
+struct Reader {
+    FILE *f;
+    bool ok = true;
+    void raw(void *p, size_t n) { ok = ok && (n == 0 || fread(p, 1, n, f) == n); }
+    template <class T> void pod(T &v) { raw(&v, sizeof(T)); }
+    template <class T> void vec(std::vector<T> &v) {
+        uint64_t n = 0;
+        pod(n);
+        if (!ok || n > (uint64_t{1} << 34) / sizeof(T)) {
+            ok = false;
+            return;
+        }
+        v.resize((size_t)n);
+        raw(v.data(), (size_t)n * sizeof(T));
+    }
+};
+
+template <class IO, class T>
+void tables_io(IO &io, T &t) {
+    io.pod(t.num_dets);
+    io.pod(t.num_obs);
+    io.pod(t.normalising_constant);
+    io.vec(t.color);
+    io.vec(t.basis);
+    io.vec(t.ignored);
+    io.vec(t.atom_dets);
+    io.vec(t.atom_obs);
+    io.vec(t.mobius_errors);
+    io.vec(t.mobius_edges);
+    io.vec(t.rgb_reps);
+    io.pod(t.drag_ambiguities);
+    io.vec(t.row_ptr);
+    io.vec(t.adj);
+    io.vec(t.ell_adj);
+    io.pod(t.ell_shift);
+    io.pod(t.min_wt);
+    io.vec(t.adj_drag);
+    io.vec(t.det_info);
+    io.vec(t.rep_obs);
+    io.vec(t.self_drag);
+    io.vec(t.ingest_mask);
+    io.vec(t.drag);
+    io.vec(t.drag_pair);
+    io.vec(t.near);
+    io.pod(t.near_stride);
+}
+
+uint64_t fnv1a(const void *p, size_t n, uint64_t h = 0xcbf29ce484222325ull) {
+    const uint8_t *b = (const uint8_t *)p;
+    for (size_t i = 0; i < n; i++) {
+        h ^= b[i];
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}
+}  // namespace
+
+void save_tables(const HostTables &t, const std::string &path, uint64_t key) {
+    // written next to the final name and renamed, so a concurrent reader never sees half a file
+    std::string tmp = path + ".tmp." + std::to_string((unsigned long long)fnv1a(&t, sizeof(void *)) ^ (unsigned long long)(uintptr_t)&t);
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    Writer w{f};
+    w.pod(CACHE_MAGIC);
+    w.pod(CACHE_VERSION);
+    w.pod(key);
+    tables_io(w, t);
+    // the charge graph is nested: flatten it
+    w.pod<uint64_t>(t.charge_graph.size());
+    for (const auto &row : t.charge_graph) w.vec(row);
+    w.pod(CACHE_MAGIC);
+    bool ok = w.ok;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+bool load_tables(HostTables &t, const std::string &path, uint64_t key) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    Reader r{f};
+    uint64_t magic = 0, version = 0, k = 0, tail = 0, rows = 0;
+    r.pod(magic);
+    r.pod(version);
+    r.pod(k);
+    bool ok = r.ok && magic == CACHE_MAGIC && version == CACHE_VERSION && k == key;
+    if (ok) {
+        tables_io(r, t);
+        r.pod(rows);
+        ok = r.ok && rows <= (uint64_t{1} << 32);
+        if (ok) {
+            t.charge_graph.resize((size_t)rows);
+            for (auto &row : t.charge_graph) r.vec(row);
+        }
+        r.pod(tail);
+        ok = ok && r.ok && tail == CACHE_MAGIC && t.row_ptr.size() == (size_t)t.num_dets * 2 + 1 &&
+             t.near.size() == (size_t)t.near_stride * t.num_dets * 2;
+    }
+    fclose(f);
+    if (!ok) t = HostTables{};
+    return ok;
+}
+
+HostTables compile_tables_cached(const std::string &dem_text, bool *from_cache) {
+    if (from_cache) *from_cache = false;
+    const char *dir = std::getenv("CHROMOBIUS_B200_CACHE");
+    if (!dir || !*dir) return compile_tables(FlatDem::parse(dem_text));
+    const char *stride_env = std::getenv("CB200_NEAR_STRIDE");
+    uint64_t key = fnv1a(dem_text.data(), dem_text.size());
+    key = fnv1a(&CACHE_VERSION, sizeof(CACHE_VERSION), key);
+    if (stride_env) key = fnv1a(stride_env, strlen(stride_env), key);
+    char name[64];
+    snprintf(name, sizeof(name), "/cb200_%016llx.tables", (unsigned long long)key);
+    const std::string path = std::string(dir) + name;
+    HostTables t;
+    if (load_tables(t, path, key)) {
+        if (from_cache) *from_cache = true;
+        return t;
+    }
+    t = compile_tables(FlatDem::parse(dem_text));
+    save_tables(t, path, key);
+    return t;
+}
+
 TablesView HostTables::view() const {
     TablesView v{};
     v.num_dets = num_dets;

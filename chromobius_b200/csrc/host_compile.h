@@ -100,6 +100,14 @@ HostTables compile_tables(const FlatDem &dem, uint32_t near_stride = NEAR_STRIDE
 // (Re)builds t.near for the given stride from t.row_ptr / t.adj (multi-threaded).
 void build_near_table(HostTables &t, uint32_t near_stride);
 
+// DEM text -> tables, through an on-disk cache when the environment variable CHROMOBIUS_B200_CACHE names a directory
+// (the compile step is paid once per DEM *per worker process*; sinter starts many). The cache key is a
+// hash of the DEM text, the table format version and the near-table setting; a file that fails its checks is ignored
+// and rewritten. `from_cache` (nullable) reports whether the tables were loaded.
+HostTables compile_tables_cached(const std::string &dem_text, bool *from_cache = nullptr);
+void save_tables(const HostTables &t, const std::string &path, uint64_t key);
+bool load_tables(HostTables &t, const std::string &path, uint64_t key);
+
 }  // namespace cb200
 
 #endif

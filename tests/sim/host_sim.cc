@@ -27,7 +27,7 @@ const char *cbsim_last_error() { return g_err.c_str(); }
 void *cbsim_compile(const char *dem_text) {
     try {
         auto *s = new Sim();
-        s->tables = compile_tables(FlatDem::parse(dem_text));
+        s->tables = compile_tables_cached(dem_text);
         return s;
     } catch (const std::exception &e) {
         g_err = e.what();

@@ -71,6 +71,34 @@ def test_blossom_layout_classes_agree(built, monkeypatch, pool_kb):
     assert (other[0] == full[0]).all() and (other[1] == full[1]).all() and (other[3] == full[3]).all()
 
 
+def test_table_cache_round_trip(built, monkeypatch, tmp_path):
+    """CHROMOBIUS_B200_CACHE: tables loaded from disk equal freshly compiled ones; damaged files are ignored and rewritten."""
+    import os
+    text = read_dem('midout_color_code_d5_r10_p1000')
+    dets, _ = NumpyDemSampler(text).sample(300, seed=6)
+    fresh = SimDecoder(text)
+    want = fresh.decode(dets)
+    monkeypatch.setenv('CHROMOBIUS_B200_CACHE', str(tmp_path))
+    first = SimDecoder(text)       # compiles and writes
+    files = os.listdir(tmp_path)
+    assert len(files) == 1 and files[0].startswith('cb200_') and files[0].endswith('.tables')
+    second = SimDecoder(text)      # loads
+    for d in (first, second):
+        got = d.decode(dets)
+        assert all((a == b).all() for a, b in zip(got, want))
+        assert d.describe() == fresh.describe() and d.mobius_dem() == fresh.mobius_dem()
+        assert all((a == b).all() for a, b in zip(d.graph(), fresh.graph()))
+    path = os.path.join(tmp_path, files[0])
+    size = os.path.getsize(path)
+    with open(path, 'r+b') as f:   # truncate: the loader must notice and recompile
+        f.truncate(size // 2)
+    third = SimDecoder(text)
+    assert all((a == b).all() for a, b in zip(third.decode(dets), want))
+    assert os.path.getsize(path) == size
+    other = SimDecoder(read_dem('surface_code_d5_r5_p1000'))   # a different DEM gets its own file
+    assert len(os.listdir(tmp_path)) == 2 and other.num_detectors != first.num_detectors
+
+
 def test_device_logic_survives_tiny_scratch(built):
     """Scratch overflow is reported per shot (status 1), never silently wrong."""
     text = read_dem('midout_color_code_d5_r10_p1000')
