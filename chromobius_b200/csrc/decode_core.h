@@ -132,6 +132,7 @@ CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { return 
 CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
 CB_HD uint32_t cb_atomic_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 CB_HD unsigned long long cb_clock() { return (unsigned long long)clock64(); }
+CB_HD uint32_t cb_load_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 #else
 CB_HD uint32_t cb_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 CB_HD uint64_t cb_atomic_add64(uint64_t *p, uint64_t v) { uint64_t o = *p; *p = o + v; return o; }
@@ -140,6 +141,7 @@ CB_HD uint32_t cb_atomic_cas(uint32_t *p, uint32_t expect, uint32_t v) { uint32_
 CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 CB_HD uint32_t cb_atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 CB_HD unsigned long long cb_clock() { return 0; }
+CB_HD uint32_t cb_load_volatile(const uint32_t *p) { return *p; }
 #endif
 
 struct PhaseTimer {
@@ -212,6 +214,8 @@ struct GroupHeader {
     uint32_t lift_cyc_top;
     uint32_t nbig;
     uint32_t nhuge;
+    uint32_t task_next;   // growth requests handed out so far (this round)
+    uint32_t pad_hdr[3];
 };
 
 // Ball tables of one warp: open-addressing hash (node -> distance, frontier position) plus the frontier itself.
@@ -1892,6 +1896,31 @@ CB_HD void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scr
     else solve_component_blossom_t<G, 0>(s, g, c, scratch);
 }
 
+// Serves growth requests [task_next, limit) of this round, one warp per request, until none is left. Requests are
+// claimed with a compare-and-swap so that a warp never takes a ticket beyond `limit` (later requests are still being
+// produced by running blossoms and are served after them).
+template <class G>
+CB_HDN void grow_some(Shot &s, const G &g, uint32_t limit) {
+    while (true) {
+        uint32_t k = NO_INDEX;
+        if (g.lane == 0) {
+            uint32_t cur = cb_load_volatile(&s.hdr->task_next);
+            while (cur < limit) {
+                const uint32_t old = cb_atomic_cas(&s.hdr->task_next, cur, cur + 1);
+                if (old == cur) {
+                    k = cur;
+                    break;
+                }
+                cur = old;
+            }
+        }
+        k = g.shfl32(k, 0);
+        if (k == NO_INDEX) return;
+        const uint32_t ev = s.grow_ev[k];
+        explore_event(s, g, ev, s.grow_to[k], s.nb_cnt[ev]);
+    }
+}
+
 template <class G>
 CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     const uint32_t M = s.M;
@@ -1940,6 +1969,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             s.hdr->ngrow = 0;
             s.hdr->nbig = 0;
             s.hdr->nhuge = 0;  // number of active events
+            s.hdr->task_next = 0;
         }
         g.sync();
         // Lazy merging: two events are joined when either has no dual yet or their duals overlap (h_i + h_j > 2 d).
@@ -2038,6 +2068,8 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             }
             g.sync();
             const uint32_t nwaves = s.hdr->bcast;
+            const uint32_t ngrow_cf = s.hdr->ngrow;  // complete: the closed-form pass ended at a barrier, no blossom has run yet
+            g.sync();
             uint32_t k0 = 0;
             for (uint32_t wave = 0; wave < nwaves; wave++) {
                 uint32_t k1 = k0;
@@ -2047,6 +2079,8 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                     solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
                 }
+                // A warp without (further) blossoms in this wave serves the growth requests the closed forms made.
+                grow_some(s, g, ngrow_cf);
                 k0 = k1;
                 g.sync();
             }
@@ -2061,10 +2095,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         g.sync();  // everyone has read the verdict before the next phase may change it
         if (st) return round;
         if (ngrow == 0) return round;
-        for (uint32_t k = g.warp; k < ngrow; k += g.nwarps) {
-            uint32_t ev = s.grow_ev[k];
-            explore_event(s, g, ev, s.grow_to[k], s.nb_cnt[ev]);
-        }
+        grow_some(s, g, ngrow);
     }
 }
 
