@@ -421,31 +421,31 @@ CB_HD void init_group_arena(Shot &s, const G &g) {
 // Exclusive prefix sum of arr[0..n) in place, cooperatively; returns the total. Needs g.n <= SCAN_TMP.
 template <class G>
 CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t n) {
+    // per-thread chunk sums -> inclusive scan inside the warp (shuffles) -> warp totals through scan_tmp
     uint32_t chunk = (n + g.n - 1) / g.n;
     uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
     if (lo > n) lo = n;
     if (hi > n) hi = n;
     uint32_t sum = 0;
     for (uint32_t k = lo; k < hi; k++) sum += arr[k];
-    s.scan_tmp[g.tid] = sum;
-    g.sync();
-    if (g.tid == 0) {
-        uint32_t run = 0;
-        for (int t = 0; t < g.n; t++) {
-            uint32_t v = s.scan_tmp[t];
-            s.scan_tmp[t] = run;
-            run += v;
-        }
-        s.hdr->scan_total = run;
+    uint32_t incl = sum;
+    for (int o = 1; o < g.lanes; o <<= 1) {
+        uint32_t t = g.shfl32(incl, g.lane >= o ? g.lane - o : g.lane);
+        if (g.lane >= o) incl += t;
     }
+    if (g.lane == g.lanes - 1) s.scan_tmp[g.warp] = incl;
     g.sync();
-    uint32_t run = s.scan_tmp[g.tid];
+    uint32_t run = incl - sum, total = 0;
+    for (int w = 0; w < g.nwarps; w++) {
+        uint32_t v = s.scan_tmp[w];
+        if (w < g.warp) run += v;
+        total += v;
+    }
     for (uint32_t k = lo; k < hi; k++) {
         uint32_t v = arr[k];
         arr[k] = run;
         run += v;
     }
-    uint32_t total = s.hdr->scan_total;
     g.sync();
     return total;
 }
@@ -923,11 +923,13 @@ CB_HDN void explore_first_near(Shot &s, const G &g) {
     const uint32_t *const words = s.words;
     for (uint32_t i = (uint32_t)g.tid; i < M; i += (uint32_t)g.n) {
         const uint32_t src = s.event_node(i);
-        for (uint32_t p = 0; p < stride; p += 2) {
-            const U4 pair = *(const U4 *)near_at(s.T, src, p);  // rows are 256-byte aligned, p is even
-            const NearEntry e[2] = {{pair.x, pair.y}, {pair.z, pair.w}};
+        for (uint32_t p = 0; p < stride; p += 4) {
+            // rows are 256-byte aligned and p is a multiple of four: two independent 16-byte loads per step
+            const U4 pair0 = *(const U4 *)near_at(s.T, src, p);
+            const U4 pair1 = *(const U4 *)near_at(s.T, src, p + 2);
+            const NearEntry e[4] = {{pair0.x, pair0.y}, {pair0.z, pair0.w}, {pair1.x, pair1.y}, {pair1.z, pair1.w}};
             bool stop = false;
-            for (int k = 0; k < 2 && !stop; k++) {
+            for (int k = 0; k < 4 && !stop; k++) {
                 if (e[k].dist_flag == NEAR_PAD) {
                     stop = true;  // the row ends without an event: the search decides (it reports an exhausted graph)
                     break;
@@ -2471,6 +2473,12 @@ CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t
 
 template <class G>
 CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
+#ifdef CB_LIFT_PROF
+    unsigned long long lp_t = cb_clock();
+#define CB_LIFT_LAP(k) if (s.prof && g.tid == 0) { unsigned long long now = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[k], now - lp_t); lp_t = now; }
+#else
+#define CB_LIFT_LAP(k)
+#endif
     const uint32_t M = s.M;
     // edge numbering: exclusive scan of (path_len - 1) over events -> s.start
     for (uint32_t i = g.tid; i < M; i += g.n) s.start[i] = s.path_len[i] ? s.path_len[i] - 1 : 0;
@@ -2541,6 +2549,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     g.sync();
     for (uint32_t e = g.tid; e < E; e += g.n) uf_union(L.uf, L.slot[2 * e], L.slot[2 * e + 1]);
     g.sync();
+    CB_LIFT_LAP(12)
     // d. list offsets
     uint32_t total = group_exclusive_scan(s, g, L.lstart, HE);
     if (g.tid == 0) L.lstart[HE] = total;
@@ -2581,6 +2590,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         }
     g.sync();
     const uint32_t ncomp = s.hdr->lift_ncomp;
+    CB_LIFT_LAP(13)
     // h. one thread per component
     for (uint32_t c = g.tid; c < ncomp; c += g.n) {
         uint32_t root = L.comps[c];
@@ -2592,9 +2602,11 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         lift_component(s, L, root, L.cyc + off);
     }
     g.sync();
+    CB_LIFT_LAP(14)
     // i. restore the persistent-clean node_slot array
     for (uint32_t q = g.tid; q < HE; q += g.n) s.node_slot[L.own[q]] = NO_INDEX;
     g.sync();
+    CB_LIFT_LAP(15)
 }
 
 // One shot, start to finish. `shot` indexes the caller's arrays.
