@@ -334,6 +334,19 @@ void launch_decode(const DecodeParams &p, uint32_t groups, uint32_t smem_per_gro
     uint32_t blocks = (groups + per_block - 1) / per_block;
     size_t smem = (size_t)smem_per_group * per_block;
     CUDA_CHECK(cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Ask for the smallest shared-memory carve-out that still holds the resident blocks (occupancy is register limited):
+    // the rest of the unified storage becomes L1, where the per-event scratch of the shots in flight lives.
+    {
+        int dev = 0, sm_bytes = 0, resident = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_decode<GROUP>, (int)threads, smem);
+        int pct = -1;
+        if (sm_bytes > 0 && resident > 0) pct = (int)(((size_t)resident * (smem + 1024) * 100 + sm_bytes - 1) / sm_bytes);
+        if (const char *env = getenv("CB200_CARVEOUT_PCT")) pct = atoi(env);  // experiments
+        if (pct >= 0) cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
+        cudaGetLastError();
+    }
     k_decode<GROUP><<<blocks, threads, smem, st>>>(p, groups, smem_per_group);
 }
 template <int GROUP>

@@ -2032,6 +2032,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         g.sync();
         pt.lap(8);
         const uint32_t nbig = s.hdr->nbig;
+#ifdef CB_WAVE_PROF
+        const unsigned long long wave_prof_before = pt.t[9];
+#endif
         // Blossom components share the group's shared-memory table space as one pool: largest first, each gets its own
         // slice, and what does not fit next to the others waits for the next wave (components beyond the whole pool use
         // the dynamic region). s.blist holds the components, s.fillp their (wave << 16 | offset / 16).
@@ -2087,6 +2090,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                 g.sync();
             }
             pt.lap(9);
+#ifdef CB_WAVE_PROF
+            if (s.prof && g.tid == 0) cb_atomic_add64((uint64_t *)&s.prof[12 + (round < 4 ? round - 1 : 3)], pt.t[9] - wave_prof_before);
+#endif
             if (s.sh_ball.H)
                 for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
         }
