@@ -2337,15 +2337,24 @@ CB_HD uint32_t find_half_edge(const TablesView &T, uint32_t from, uint32_t to) {
 }
 
 // decoder.cc:80-138. `used` bookkeeping is a per-detection-event flag instead of a linear search.
-CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len, uint32_t start, uint64_t *out) {
+// cyc_di[k] is the DragEntry index of the step that arrives at cycle[k] (the drag-table lookup of the reference's
+// `mmm.find`, precomputed per edge by lift_shot). Nothing the loop loads depends on the running charge state except the
+// observable mask itself, so the next step's node, drag index and valid bits are fetched one step ahead.
+CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, const uint32_t *cyc_di, uint32_t len, uint32_t start, uint64_t *out) {
     OptMask cur;
     cur.has = 1u << start;
     cur.v[0] = cur.v[1] = cur.v[2] = cur.v[3] = 0;
     uint32_t cur_node = cycle[len - 1];
     uint32_t cur_loc = cur_node >> 1;
+    uint32_t pf_node = cycle[0], pf_di = cyc_di[0];
     for (uint32_t k = 0; k < len; k++) {
-        uint32_t next_node = cycle[k];
-        uint32_t next_loc = next_node >> 1;
+        const uint32_t next_node = pf_node, di = pf_di;
+        const uint32_t next_loc = next_node >> 1;
+        const uint32_t valid = di != NO_INDEX ? s.T.drag[di].valid : 0;
+        if (k + 1 < len) {
+            pf_node = cycle[k + 1];
+            pf_di = cyc_di[k + 1];
+        }
         bool has_event = s.node_is_event(cur_node);
         uint32_t evi = has_event ? (s.node_event_index(cur_node) >> 1) : 0;
         OptMask after;
@@ -2367,26 +2376,16 @@ CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, uint32_t len,
                 if (cur.has & (1u << c1)) { after.v[c2] = cur.v[c1] ^ f; after.has |= 1u << c2; }
                 if (cur.has & (1u << c2)) { after.v[c1] = cur.v[c2] ^ f; after.has |= 1u << c1; }
             }
-        } else {
-            uint32_t di = NO_INDEX;
-            bool forward = true;  // walking the stored (min, max) orientation
-            if (cur_loc == next_loc) {
-                di = s.T.self_drag[cur_loc];
-            } else {
-                uint32_t e = find_half_edge(s.T, cur_node, next_node);
-                if (e != NO_INDEX) di = s.T.adj_drag[e];
-                forward = cur_loc < next_loc;
-            }
-            if (di != NO_INDEX) {
-                const DragEntry &de = s.T.drag[di];
-                for (uint32_t cc = 0; cc < 4; cc++) {
-                    if (!(cur.has & (1u << cc))) continue;
-                    for (uint32_t nc = 0; nc < 4; nc++) {
-                        uint32_t bit = forward ? 4 * cc + nc : 4 * nc + cc;
-                        if (de.valid & (1u << bit)) {
-                            after.v[nc] = cur.v[cc] ^ de.obs[bit];
-                            after.has |= 1u << nc;
-                        }
+        } else if (di != NO_INDEX) {
+            const bool forward = cur_loc <= next_loc;  // walking the stored (min, max) orientation
+            const DragEntry &de = s.T.drag[di];
+            for (uint32_t cc = 0; cc < 4; cc++) {
+                if (!(cur.has & (1u << cc))) continue;
+                for (uint32_t nc = 0; nc < 4; nc++) {
+                    uint32_t bit = forward ? 4 * cc + nc : 4 * nc + cc;
+                    if (valid & (1u << bit)) {
+                        after.v[nc] = cur.v[cc] ^ de.obs[bit];
+                        after.has |= 1u << nc;
                     }
                 }
             }
@@ -2419,57 +2418,95 @@ struct LiftArrays {
     uint32_t *cedges;   // [HE] per component root: number of edges
     uint32_t *comps;    // [HE] list of component roots
     uint32_t *cyc;      // cycle buffers
+    uint32_t *cyc_e;    // parallel to cyc: the edge that arrives at cyc[k]; replaced by its drag index before the discharge
+    uint32_t *mate;     // [HE] the other half-edge at own[q] when that node has exactly two, else NO_INDEX
+    uint32_t *edrag;    // [E] DragEntry index of edge e (self-drag entry for an edge inside one detector), NO_INDEX: none
     uint8_t *dead;      // [HE] voided list positions
+    uint8_t *simple;    // [HE] per component root: every node has exactly two half-edges (the component is one plain cycle)
     uint32_t HE, EM;    // half-edges, matched edges
 };
 
 // Tours and discharges one component. Runs on one thread.
-CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc) {
-    auto look_next = [&](uint32_t sl) -> uint32_t {  // euler_tours.cc:34-45
-        while (true) {
-            uint32_t p = L.lstart[sl] + L.fillc[sl];
-            if (p >= L.lstart[sl + 1]) return NO_INDEX;
-            if (L.dead[p]) {
-                L.fillc[sl]++;
-                continue;
-            }
-            return p;
-        }
-    };
-    uint32_t n0 = L.own[L.cmin[root]];
+CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc, uint32_t *cyc_e) {
     uint32_t clen = 0;
-    cyc[clen++] = n0;
-    while (true) {
-        // extend_cycle_depth_first (euler_tours.cc:64-76)
+    if (L.simple[root]) {
+        // Every node has two half-edges: the component is one plain cycle and the reference's depth-first extension
+        // (euler_tours.cc:64-76) just walks it, starting at the first node along its first half-edge -- the smallest
+        // matched half-edge of the component. One dependent load per step instead of the list bookkeeping below.
+        const uint32_t q0 = L.cmin[root];
+        const uint32_t n0 = L.own[q0];
+        cyc[clen++] = n0;
+        uint32_t q = q0;
         while (true) {
-            uint32_t sl = s.node_slot[cyc[clen - 1]];
-            uint32_t p = look_next(sl);
-            if (p == NO_INDEX) break;
-            L.fillc[sl]++;
-            uint32_t q = L.lst[p];
-            cyc[clen++] = L.own[q ^ 1];
-            L.dead[L.pos_of[q ^ 1]] = 1;
+            const uint32_t far = q ^ 1;
+            const uint32_t node = L.own[far];
+            const uint32_t nq = L.mate[far];
+            if (node == n0) {
+                cyc_e[0] = q >> 1;  // the closing edge arrives at the first node
+                break;
+            }
+            cyc_e[clen] = q >> 1;
+            cyc[clen++] = node;
+            q = nq;
+            if (clen > L.cedges[root] + 1) {
+                s.fail(SHOT_EULER_FAILED);
+                return;
+            }
         }
-        // rotate_cycle_to_end_with_unfinished_node (euler_tours.cc:78-97)
-        if (cyc[clen - 1] != cyc[0]) {
-            s.fail(SHOT_EULER_FAILED);
-            return;
+    } else {
+        auto look_next = [&](uint32_t sl) -> uint32_t {  // euler_tours.cc:34-45
+            while (true) {
+                uint32_t p = L.lstart[sl] + L.fillc[sl];
+                if (p >= L.lstart[sl + 1]) return NO_INDEX;
+                if (L.dead[p]) {
+                    L.fillc[sl]++;
+                    continue;
+                }
+                return p;
+            }
+        };
+        uint32_t n0 = L.own[L.cmin[root]];
+        cyc[clen++] = n0;
+        cyc_e[0] = NO_INDEX;
+        while (true) {
+            // extend_cycle_depth_first (euler_tours.cc:64-76)
+            while (true) {
+                uint32_t sl = s.node_slot[cyc[clen - 1]];
+                uint32_t p = look_next(sl);
+                if (p == NO_INDEX) break;
+                L.fillc[sl]++;
+                uint32_t q = L.lst[p];
+                cyc_e[clen] = q >> 1;
+                cyc[clen++] = L.own[q ^ 1];
+                L.dead[L.pos_of[q ^ 1]] = 1;
+            }
+            // rotate_cycle_to_end_with_unfinished_node (euler_tours.cc:78-97)
+            if (cyc[clen - 1] != cyc[0]) {
+                s.fail(SHOT_EULER_FAILED);
+                return;
+            }
+            clen--;
+            cyc_e[0] = cyc_e[clen];  // the dropped duplicate of the first node carried its arrival edge
+            uint32_t ck = 1;
+            while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
+            if (ck >= clen) break;
+            // cyc = cyc[ck:] + cyc[:ck+1]; the arrival edges move with their nodes
+            for (uint32_t *arr : {cyc, cyc_e}) {
+                for (uint32_t a = 0, b = ck - 1; a < b; ++a, --b) { uint32_t t = arr[a]; arr[a] = arr[b]; arr[b] = t; }
+                for (uint32_t a = ck, b = clen - 1; a < b; ++a, --b) { uint32_t t = arr[a]; arr[a] = arr[b]; arr[b] = t; }
+                for (uint32_t a = 0, b = clen - 1; a < b; ++a, --b) { uint32_t t = arr[a]; arr[a] = arr[b]; arr[b] = t; }
+            }
+            cyc[clen] = cyc[0];
+            cyc_e[clen] = cyc_e[0];
+            clen++;
         }
-        clen--;
-        uint32_t ck = 1;
-        while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
-        if (ck >= clen) break;
-        // cyc = cyc[ck:] + cyc[:ck+1]
-        for (uint32_t a = 0, b = ck - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-        for (uint32_t a = ck, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-        for (uint32_t a = 0, b = clen - 1; a < b; ++a, --b) { uint32_t t = cyc[a]; cyc[a] = cyc[b]; cyc[b] = t; }
-        cyc[clen] = cyc[0];
-        clen++;
     }
+    // arrival edges -> drag indices (independent loads, pipelined by the hardware)
+    for (uint32_t k = 0; k < clen; k++) cyc_e[k] = L.edrag[cyc_e[k]];
     // discharge_cycle (decoder.cc:140-203): start charges N, R, G, B; the first that closes wins
     for (uint32_t c = 0; c < 4; c++) {
         uint64_t v;
-        if (discharge_single_start(s, cyc, clen, c, &v)) {
+        if (discharge_single_start(s, cyc, cyc_e, clen, c, &v)) {
             if (v) cb_atomic_xor64(&s.hdr->obs, v);
             return;
         }
@@ -2495,7 +2532,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     L.HE = 2 * E;
     const uint32_t HE = L.HE;
     if (g.tid == 0) {
-        uint8_t *mem = s.alloc((uint64_t{HE} * 10 + 1) * 4 + 16 * 12 + (uint64_t{3} * E + 8) * 4 + HE);
+        uint8_t *mem = s.alloc((uint64_t{HE} * 11 + 1) * 4 + 16 * 16 + (uint64_t{3} * E + 8) * 8 + uint64_t{E} * 4 + uint64_t{HE} * 2);
         s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
         s.hdr->lift_ncomp = 0;
         s.hdr->lift_cyc_top = 0;
@@ -2507,11 +2544,14 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     if (!moff) return;
     {
         uint8_t *p = s.dyn + ((uint64_t)(moff - 1) << 4);
-        uint32_t **arrs[] = {&L.own, &L.slot, &L.fillc, &L.lst, &L.pos_of, &L.uf, &L.cmin, &L.cedges, &L.comps};
+        uint32_t **arrs[] = {&L.own, &L.slot, &L.fillc, &L.lst, &L.pos_of, &L.uf, &L.cmin, &L.cedges, &L.comps, &L.mate};
         for (auto a : arrs) { *a = (uint32_t *)p; p += align16(uint64_t{HE} * 4); }
         L.lstart = (uint32_t *)p; p += align16((uint64_t{HE} + 1) * 4);
         L.cyc = (uint32_t *)p; p += align16((uint64_t{3} * E + 8) * 4);
-        L.dead = p;
+        L.cyc_e = (uint32_t *)p; p += align16((uint64_t{3} * E + 8) * 4);
+        L.edrag = (uint32_t *)p; p += align16(uint64_t{E} * 4);
+        L.dead = p; p += align16(uint64_t{HE});
+        L.simple = p;
     }
     // a. endpoints of every half-edge
     for (uint32_t i = g.tid; i < M; i += g.n) {
@@ -2544,6 +2584,8 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         L.cmin[q] = NO_INDEX;
         L.cedges[q] = 0;
         L.dead[q] = 0;
+        L.mate[q] = NO_INDEX;
+        L.simple[q] = 1;
     }
     g.sync();
     // c. degrees and connectivity
@@ -2553,7 +2595,19 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         cb_atomic_add(&L.lstart[sl], 1);
     }
     g.sync();
-    for (uint32_t e = g.tid; e < E; e += g.n) uf_union(L.uf, L.slot[2 * e], L.slot[2 * e + 1]);
+    for (uint32_t e = g.tid; e < E; e += g.n) {
+        uf_union(L.uf, L.slot[2 * e], L.slot[2 * e + 1]);
+        // the drag-table entry the discharge will need for this edge (decoder.cc:104-127: mmm.find of the detector pair)
+        const uint32_t a = L.own[2 * e], b = L.own[2 * e + 1];
+        uint32_t di;
+        if ((a >> 1) == (b >> 1)) {
+            di = s.T.self_drag[a >> 1];
+        } else {
+            const uint32_t he = find_half_edge(s.T, a, b);
+            di = he != NO_INDEX ? s.T.adj_drag[he] : NO_INDEX;
+        }
+        L.edrag[e] = di;
+    }
     g.sync();
     CB_LIFT_LAP(12)
     // d. list offsets
@@ -2582,6 +2636,12 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
             }
             for (uint32_t a = a0; a < a1; a++) L.pos_of[L.lst[a]] = a;
             L.fillc[q] = 0;  // becomes next_neighbor
+            if (a1 - a0 == 2) {
+                L.mate[L.lst[a0]] = L.lst[a0 + 1];
+                L.mate[L.lst[a0 + 1]] = L.lst[a0];
+            } else {
+                L.simple[uf_find(L.uf, q)] = 0;
+            }
         }
         uint32_t r = uf_find(L.uf, L.slot[q]);
         if (q < 2 * L.EM) cb_atomic_min(&L.cmin[r], q);
@@ -2605,7 +2665,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
             s.fail(SHOT_EULER_FAILED);
             continue;
         }
-        lift_component(s, L, root, L.cyc + off);
+        lift_component(s, L, root, L.cyc + off, L.cyc_e + off);
     }
     g.sync();
     CB_LIFT_LAP(14)
