@@ -976,7 +976,7 @@ constexpr int BLOSSOM_PAR_MIN = CB_BLOSSOM_PAR_MIN;  // components with at least
 
 template <class G, int CAP = 0>
 struct Blossom {
-    enum Op : uint32_t { OP_EXIT = 0, OP_INIT, OP_SET_SLACK, OP_DUAL_MIN, OP_LAB_UPDATE, OP_NEXT_TIGHT, OP_BLOSSOM_CLEAR, OP_MERGE_ROW, OP_PHASE_INIT };
+    enum Op : uint32_t { OP_EXIT = 0, OP_SET_SLACK, OP_DUAL_MIN, OP_LAB_UPDATE, OP_NEXT_TIGHT, OP_BLOSSOM_CLEAR, OP_MERGE_ROW, OP_PHASE_INIT };
     int n, n_x, NX, FL, AW;
     // Storage. CAP == 0: sized for n at run time, addressed through the pointers below (any memory). CAP > 0: sized for CAP
     // vertices at compile time, every array at a constant offset from the object itself, which then always lives in shared
@@ -1116,12 +1116,19 @@ struct Blossom {
             ((uint16_t *)ge())[(a * nxs() + b) * 2] = (uint16_t)eu;
             ((uint16_t *)ge())[(a * nxs() + b) * 2 + 1] = (uint16_t)ev;
         } else {
-            ge()[(a * nxs() + b) * 2] = (uint8_t)eu;
-            ge()[(a * nxs() + b) * 2 + 1] = (uint8_t)ev;
+            ((uint16_t *)ge())[a * nxs() + b] = (uint16_t)(eu | (ev << 8));  // both bytes with one store
         }
     }
     CB_HD int64_t edist(int a, int b) {  // slack of the best edge between nodes a and b
-        int eu = geu(a, b), ev = gev(a, b);
+        int eu, ev;
+        if (is_wide()) {
+            eu = geu(a, b);
+            ev = gev(a, b);
+        } else {
+            const uint32_t pair = ((const uint16_t *)ge())[a * nxs() + b];
+            eu = (int)(pair & 0xFF);
+            ev = (int)(pair >> 8);
+        }
         return lab()[eu] + lab()[ev] - 2 * W()[eu * ws() + ev];
     }
     CB_HD uint16_t *flower(int b) { return fl() + (b - n) * fls(); }
@@ -1143,17 +1150,21 @@ struct Blossom {
         CB_LOOP
         for (int u = 1 + lane; u <= n; u += lanes) {
             CB_LOOP
-            for (int k = 0; k < aws(); k++) adjm()[u * aws() + k] = 0;
-            CB_LOOP
-            for (int v = 1; v <= n; ++v) {
-                ffrom(u, v) = (uint16_t)(u == v ? u : 0);
-                int64_t x = W()[u * ws() + v];
-                if (x > 0) {
-                    set_ge(u, v, u, v);
-                    adjm()[u * aws() + (v >> 5)] |= 1u << (v & 31);
-                } else {
-                    set_ge(u, v, 0, 0);
+            for (int k = 0; k < aws(); k++) {
+                uint32_t acc = 0;  // adjacency bits of this 32-vertex chunk, stored once
+                const int v0 = k ? 32 * k : 1, v1 = 32 * k + 31 < n ? 32 * k + 31 : n;
+                CB_LOOP
+                for (int v = v0; v <= v1; ++v) {
+                    ffrom(u, v) = (uint16_t)(u == v ? u : 0);
+                    int64_t x = W()[u * ws() + v];
+                    if (x > 0) {
+                        set_ge(u, v, u, v);
+                        acc |= 1u << (v & 31);
+                    } else {
+                        set_ge(u, v, 0, 0);
+                    }
                 }
+                adjm()[u * aws() + k] = acc;
             }
         }
     }
@@ -1251,11 +1262,6 @@ struct Blossom {
         const int lane = g.lane, lanes = g.lanes;
         uint64_t r = 0;
         switch (op) {
-            case OP_INIT:
-                k_init(lane, lanes);
-                g.wsync();  // k_init clears lab()[] with a different lane-to-vertex mapping
-                k_row_max_lab(lane, lanes);
-                break;
             case OP_SET_SLACK:
                 r = g.min64(k_set_slack(lane, lanes, (int)a0));
                 break;
@@ -1602,16 +1608,20 @@ struct Blossom {
         }
     }
     // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match()[1..n] = partners.
+    // Every lane of the warp: per-vertex state, edge endpoints, adjacency rows and the starting labels (all O(n^2), data
+    // parallel). W must be filled. Ends with the lanes synchronised.
+    CB_HD void prepare(const G &g) {
+        in_shared();
+        k_init(g.lane, g.lanes);
+        g.wsync();  // k_init clears lab[] with a different lane-to-vertex mapping
+        k_row_max_lab(g.lane, g.lanes);
+        g.wsync();
+    }
+    // Master only, after prepare().
     CB_HDN int solve(const G &g) {
         in_shared();
         n_x = n;
         vis_t = 0;
-        if (is_par()) {
-            call(g, OP_INIT);
-        } else {
-            k_init(0, 1);
-            k_row_max_lab(0, 1);
-        }
         // Greedy start on the edges that are tight under the row-maximum labels (mutual best partners), lowest indices
         // first: a valid primal-dual state that leaves only the remaining vertices to the augmentation phases.
         int cnt = 0;
@@ -1863,6 +1873,7 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     g.wsync();
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     const int64_t big = blossom_fill_weights(s, g, r, n, mem, bl.W(), (uint32_t)bl.ws());
+    bl.prepare(g);
     uint32_t pairs = 0;
     if (g.lane == 0) {
         pairs = (uint32_t)bl.solve(g);
