@@ -194,11 +194,11 @@ CB_HD uint32_t ctz32(uint32_t v) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Memory of one group.
-//   arena (global): [GroupHeader][scan_tmp][per-warp fallback ball tables][node_slot: u32 x num_nodes]
+//   arena (global): [GroupHeader][scan_tmp][per-warp fallback ball tables]
 //                   [per-event arrays][dynamic region]
 //   shared        : [masked row words][word ranks][per-warp ball tables]
 // Persistent-clean invariants (established by init_group_arena / init_group_shared, restored by every user):
-//   every ball-table key == HT_EMPTY, every node_slot == NO_INDEX.
+//   every ball-table key == HT_EMPTY.
 // ---------------------------------------------------------------------------------------------------------------
 struct GroupHeader {
     uint32_t status;
@@ -273,7 +273,7 @@ CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets,
 }
 CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t nwarps) {
     return align16(sizeof(GroupHeader)) + align16(SCAN_TMP * 4) + nwarps * ball_table_bytes(c.ht_log2, c.found_cap) +
-           align16(uint64_t{num_nodes} * 4) + event_bytes(c) + align16(c.dyn_bytes);
+           event_bytes(c) + align16(c.dyn_bytes);
 }
 
 // Everything one group needs to decode one shot. Every thread of the group holds an identical copy (pointers are
@@ -287,7 +287,6 @@ struct Shot {
     uint8_t *sh_tables;    // all warps' shared-memory tables, contiguous: the blossom scratch pool between ball phases
     uint64_t sh_tables_bytes;
     BallTables gl_ball;    // this warp's global-memory fallback tables
-    uint32_t *node_slot;   // [num_nodes] persistent-clean
     uint32_t *words;       // masked detection-event bits as little-endian u32 words (shared memory)
     uint32_t *word_rank;   // [nwords + 1] exclusive prefix popcount (shared memory)
     uint32_t nwords;
@@ -368,7 +367,6 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     uint64_t gb = ball_table_bytes(p.cfg.ht_log2, p.cfg.found_cap);
     bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp * gb, p.cfg.ht_log2, p.cfg.found_cap);
     q += (uint64_t)g.nwarps * gb;
-    s.node_slot = (uint32_t *)q; q += align16(uint64_t{p.T.num_nodes} * 4);
     uint64_t m = p.cfg.max_events;
     s.evdet = (uint32_t *)q; q += align16(m * 4);
     s.R = (int64_t *)q; q += align16(m * 8);
@@ -414,7 +412,6 @@ CB_HD void init_group_shared(Shot &s, const G &g) {
 template <class G>
 CB_HD void init_group_arena(Shot &s, const G &g) {
     for (uint32_t k = g.lane; k < s.gl_ball.H; k += g.lanes) s.gl_ball.key[k] = HT_EMPTY;
-    for (uint32_t k = g.tid; k < s.T.num_nodes; k += g.n) s.node_slot[k] = NO_INDEX;
     g.sync();
 }
 
@@ -2432,10 +2429,28 @@ struct LiftArrays {
     uint32_t *cyc_e;    // parallel to cyc: the edge that arrives at cyc[k]; replaced by its drag index before the discharge
     uint32_t *mate;     // [HE] the other half-edge at own[q] when that node has exactly two, else NO_INDEX
     uint32_t *edrag;    // [E] DragEntry index of edge e (self-drag entry for an edge inside one detector), NO_INDEX: none
+    uint32_t *node_min; // [M + HK] smallest half-edge per compact node id: event nodes by event index, the other (path
+                        // interior) nodes by their slot in the hash below + M
+    uint32_t *hkey;     // [HK] open-addressing hash of the interior nodes (HK a power of two)
+    uint32_t HK, M;
     uint8_t *dead;      // [HE] voided list positions
     uint8_t *simple;    // [HE] per component root: every node has exactly two half-edges (the component is one plain cycle)
     uint32_t HE, EM;    // half-edges, matched edges
 };
+
+// Compact id of a node that takes part in the shot's Euler graph (see LiftArrays::node_min). `insert` adds unknown
+// interior nodes; lookups of nodes that were never inserted return NO_INDEX.
+CB_HD uint32_t lift_node_id(Shot &s, const LiftArrays &L, uint32_t node, bool insert) {
+    if (s.node_is_event(node)) return s.node_event_index(node);
+    uint32_t k = ht_hash(node, L.HK);
+    while (true) {
+        uint32_t cur = insert ? cb_atomic_cas(&L.hkey[k], HT_EMPTY, node) : L.hkey[k];
+        if (cur == node || (insert && cur == HT_EMPTY)) return L.M + k;
+        if (cur == HT_EMPTY) return NO_INDEX;
+        k = (k + 1) & (L.HK - 1);
+    }
+}
+CB_HD uint32_t lift_node_slot(Shot &s, const LiftArrays &L, uint32_t node) { return L.node_min[lift_node_id(s, L, node, false)]; }
 
 // Tours and discharges one component. Runs on one thread.
 CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t *cyc, uint32_t *cyc_e) {
@@ -2482,7 +2497,7 @@ CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t
         while (true) {
             // extend_cycle_depth_first (euler_tours.cc:64-76)
             while (true) {
-                uint32_t sl = s.node_slot[cyc[clen - 1]];
+                uint32_t sl = lift_node_slot(s, L, cyc[clen - 1]);
                 uint32_t p = look_next(sl);
                 if (p == NO_INDEX) break;
                 L.fillc[sl]++;
@@ -2499,7 +2514,7 @@ CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t
             clen--;
             cyc_e[0] = cyc_e[clen];  // the dropped duplicate of the first node carried its arrival edge
             uint32_t ck = 1;
-            while (ck < clen && look_next(s.node_slot[cyc[ck]]) == NO_INDEX) ck++;
+            while (ck < clen && look_next(lift_node_slot(s, L, cyc[ck])) == NO_INDEX) ck++;
             if (ck >= clen) break;
             // cyc = cyc[ck:] + cyc[:ck+1]; the arrival edges move with their nodes
             for (uint32_t *arr : {cyc, cyc_e}) {
@@ -2542,8 +2557,13 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     const uint32_t E = L.EM + M / 2;
     L.HE = 2 * E;
     const uint32_t HE = L.HE;
+    // every pair has one path: at most EM - M/2 interior nodes
+    L.M = M;
+    L.HK = 16;
+    while (L.HK < 2 * (L.EM > M / 2 ? L.EM - M / 2 : 0)) L.HK <<= 1;
     if (g.tid == 0) {
-        uint8_t *mem = s.alloc((uint64_t{HE} * 11 + 1) * 4 + 16 * 16 + (uint64_t{3} * E + 8) * 8 + uint64_t{E} * 4 + uint64_t{HE} * 2);
+        uint8_t *mem = s.alloc((uint64_t{HE} * 11 + 1) * 4 + 16 * 20 + (uint64_t{3} * E + 8) * 8 + uint64_t{E} * 4 + uint64_t{HE} * 2 +
+                               (uint64_t{M} + 2 * uint64_t{L.HK}) * 4);
         s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
         s.hdr->lift_ncomp = 0;
         s.hdr->lift_cyc_top = 0;
@@ -2562,8 +2582,12 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         L.cyc_e = (uint32_t *)p; p += align16((uint64_t{3} * E + 8) * 4);
         L.edrag = (uint32_t *)p; p += align16(uint64_t{E} * 4);
         L.dead = p; p += align16(uint64_t{HE});
-        L.simple = p;
+        L.simple = p; p += align16(uint64_t{HE});
+        L.node_min = (uint32_t *)p; p += align16((uint64_t{M} + L.HK) * 4);
+        L.hkey = (uint32_t *)p;
     }
+    for (uint32_t k = g.tid; k < M + L.HK; k += g.n) L.node_min[k] = NO_INDEX;
+    for (uint32_t k = g.tid; k < L.HK; k += g.n) L.hkey[k] = HT_EMPTY;
     // a. endpoints of every half-edge
     for (uint32_t i = g.tid; i < M; i += g.n) {
         uint32_t len = s.path_len[i];
@@ -2588,7 +2612,9 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     g.sync();
     // b. list id of a node = its smallest half-edge
     for (uint32_t q = g.tid; q < HE; q += g.n) {
-        cb_atomic_min(&s.node_slot[L.own[q]], q);
+        const uint32_t id = lift_node_id(s, L, L.own[q], true);
+        L.slot[q] = id;  // compact node id for now, the list id after the next pass
+        cb_atomic_min(&L.node_min[id], q);
         L.lstart[q] = 0;
         L.fillc[q] = 0;
         L.uf[q] = q;
@@ -2601,7 +2627,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     g.sync();
     // c. degrees and connectivity
     for (uint32_t q = g.tid; q < HE; q += g.n) {
-        uint32_t sl = s.node_slot[L.own[q]];
+        uint32_t sl = L.node_min[L.slot[q]];
         L.slot[q] = sl;
         cb_atomic_add(&L.lstart[sl], 1);
     }
@@ -2680,9 +2706,6 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     }
     g.sync();
     CB_LIFT_LAP(14)
-    // i. restore the persistent-clean node_slot array
-    for (uint32_t q = g.tid; q < HE; q += g.n) s.node_slot[L.own[q]] = NO_INDEX;
-    g.sync();
     CB_LIFT_LAP(15)
 }
 
