@@ -359,13 +359,20 @@ class _ChromobiusSinterDecoder:
 
     def compile_decoder_for_dem(self, *, dem):
         # The sinter path skips the type check (sinter_compat.pybind.cc:134-136).
+        # With CHROMOBIUS_B200_SERVICE set, the worker shares one GPU-owning process (chromobius_b200/service.py).
+        from . import service
+        address = service.service_address()
+        if address:
+            return service.RemoteCompiledDecoder(address, str(dem))
         return _ChromobiusSinterCompiledDecoder(_compile_text(str(dem)))
 
     def decode_via_files(self, *, num_shots, num_dets, num_obs, dem_path, dets_b8_in_path, obs_predictions_b8_out_path,
                          tmp_dir=None):
         """b8 in, b8 out through files (sinter_compat.pybind.cc:96-132), decoded as one GPU batch."""
+        from . import service
         with open(str(dem_path)) as f:
-            decoder = _compile_text(f.read())
+            address = service.service_address()
+            decoder = service.RemoteCompiledDecoder(address, f.read()) if address else _compile_text(f.read())
         nb = (int(num_dets) + 7) // 8
         ob = (int(num_obs) + 7) // 8
         raw = np.fromfile(str(dets_b8_in_path), dtype=np.uint8, count=int(num_shots) * nb)
