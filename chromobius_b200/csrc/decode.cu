@@ -405,6 +405,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     uint32_t gl = std::min<uint32_t>(full, 14 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
     pl.cfg.sh_pool = near ? d->tune_pool_bytes : 0;
+    if (const char *env = getenv("CB200_SH_EVENTS")) pl.cfg.sh_events = (uint32_t)strtoul(env, nullptr, 10);  // experiments
     if (const char *env = getenv("CB200_POOL_KB")) pl.cfg.sh_pool = near ? (uint32_t)strtoul(env, nullptr, 10) << 10 : 0;  // experiments
     pl.cfg.sh_found = 16;
     pl.cfg.ht_log2 = gl;

@@ -88,6 +88,9 @@ struct ScratchConfig {
     uint32_t max_events;  // matcher events (2 x detection events) per shot the arena is sized for
     uint32_t sh_pool;     // bytes of shared memory for blossom scratch (shares its space with the shared ball tables)
     uint64_t dyn_bytes;   // dynamic region (neighbour lists, blossom scratch, paths, Euler arrays)
+    uint32_t sh_events;   // per-event arrays kept in shared memory instead of the arena: bit 0 uf + root, bit 1 pc + the
+                          // flag bytes, bit 2 h (each only when max_events entries fit the launch's shared memory)
+    uint32_t pad;
 };
 
 // Launch-wide parameters.
@@ -142,6 +145,14 @@ CB_HD uint32_t cb_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v >
 CB_HD uint32_t cb_atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 CB_HD unsigned long long cb_clock() { return 0; }
 CB_HD uint32_t cb_load_volatile(const uint32_t *p) { return *p; }
+#endif
+
+// Experimental sub-phase timers (compile with -DCB_XPROF): thread 0 of a group adds the cycles since the previous lap to
+// phase_cycles[slot]; the slots 12..15 are borrowed from the blossom counters.
+#ifdef CB_XPROF
+#define CB_XLAP(s, g, t, slot) if ((s).prof && (g).tid == 0) { unsigned long long now_ = cb_clock(); cb_atomic_add64((uint64_t *)&(s).prof[slot], now_ - (t)); (t) = now_; }
+#else
+#define CB_XLAP(s, g, t, slot)
 #endif
 
 struct PhaseTimer {
@@ -269,7 +280,11 @@ CB_HD uint64_t event_bytes(const ScratchConfig &c) {
 CB_HD uint64_t shared_bytes_per_group(const ScratchConfig &c, uint32_t num_dets, uint32_t nwarps) {
     uint64_t nwords = (uint64_t{num_dets} + 31) / 32;
     uint64_t tables = nwarps * ball_table_bytes(c.sh_ht_log2, c.sh_found), pool = align16(c.sh_pool);
-    return align16(nwords * 4) + align16((nwords + 1) * 4) + (tables > pool ? tables : pool);
+    uint64_t m = c.max_events, ev = 0;
+    if (c.sh_events & 1) ev += align16(m * 4) * 2;
+    if (c.sh_events & 2) ev += align16(m * 4) + align16(m) * 4;
+    if (c.sh_events & 4) ev += align16(m * 8);
+    return align16(nwords * 4) + align16((nwords + 1) * 4) + (tables > pool ? tables : pool) + ev;
 }
 CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes, uint32_t nwarps) {
     return align16(sizeof(GroupHeader)) + align16(SCAN_TMP * 4) + nwarps * ball_table_bytes(c.ht_log2, c.found_cap) +
@@ -400,6 +415,23 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.sh_tables = sh;
     s.sh_tables_bytes = (uint64_t)g.nwarps * sb;
     if (align16(p.cfg.sh_pool) > s.sh_tables_bytes) s.sh_tables_bytes = align16(p.cfg.sh_pool);
+    // hot per-event arrays in shared memory (every pass of a matcher round re-reads them right after other threads of
+    // the group wrote them, which always misses L1)
+    sh += s.sh_tables_bytes;
+    if (p.cfg.sh_events & 1) {
+        s.uf = (uint32_t *)sh; sh += align16(m * 4);
+        s.root = (uint32_t *)sh; sh += align16(m * 4);
+    }
+    if (p.cfg.sh_events & 2) {
+        s.pc = (uint32_t *)sh; sh += align16(m * 4);
+        s.solved = sh; sh += align16(m);
+        s.regrown = sh; sh += align16(m);
+        s.stale = sh; sh += align16(m);
+        s.comp_dirty = sh; sh += align16(m);
+    }
+    if (p.cfg.sh_events & 4) {
+        s.h = (int64_t *)sh; sh += align16(m * 8);
+    }
 }
 
 // Called once per group before the first shot of a launch (shared memory does not survive launches).
@@ -1949,9 +1981,21 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
     }
     if (g.tid == 0) s.hdr->ncomp = 0;
     g.sync();
+#ifdef CB_XPROF
+    unsigned long long xt = cb_clock();
+#endif
     explore_first_near(s, g);
-    for (uint32_t i = g.warp; i < M; i += g.nwarps)
-        if (s.nb_cnt[i] == 0) explore_event(s, g, i, -1, 0);
+    CB_XLAP(s, g, xt, 12)
+    // the few events whose row held no event: one warp each (the lanes look at 32 events at a time)
+    for (uint32_t base = (uint32_t)g.warp * (uint32_t)g.lanes; base < M; base += (uint32_t)(g.nwarps * g.lanes)) {
+        const uint32_t i = base + (uint32_t)g.lane;
+        uint32_t todo = g.ballot(i < M && s.nb_cnt[i] == 0);
+        while (todo) {
+            explore_event(s, g, base + ctz32(todo), -1, 0);
+            todo &= todo - 1;
+        }
+    }
+    CB_XLAP(s, g, xt, 13)
     uint32_t round = 0;
     uint32_t *const act = s.lidx;  // events of this round's dirty components (lidx is only used inside the blossom solves)
     while (true) {
@@ -2045,7 +2089,8 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
 #endif
         // Blossom components share the group's shared-memory table space as one pool: largest first, each gets its own
         // slice, and what does not fit next to the others waits for the next wave (components beyond the whole pool use
-        // the dynamic region). s.blist holds the components, s.fillp their (wave << 16 | offset / 16).
+        // the dynamic region). s.blist holds the components, s.fillp their pool offset / 16 (0xFFFF: dynamic region),
+        // s.scan_tmp the first blossom of every wave.
         if (nbig) {
             // order: (size descending, root ascending), by counting predecessors -- one thread per component.
             // s.path_off (unused until the path phase) receives the ordered list, s.fillp the sizes.
@@ -2064,37 +2109,37 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                 const uint64_t pool = s.sh_tables_bytes;
                 uint32_t wave = 0;
                 uint64_t top = 0;
+                s.scan_tmp[0] = 0;  // scan_tmp[w] = first blossom of wave w
                 for (uint32_t k = 0; k < nbig; k++) {
                     const uint64_t need = align16(blossom_bytes<G>(s.fillp[k]));
                     if (need > pool) {
-                        s.fillp[k] = (wave << 16) | 0xFFFFu;
+                        s.fillp[k] = 0xFFFFu;
                         continue;
                     }
-                    if (top + need > pool) {
+                    if (top + need > pool && wave + 2 < SCAN_TMP) {
                         wave++;
                         top = 0;
+                        s.scan_tmp[wave] = k;
                     }
-                    s.fillp[k] = (wave << 16) | (uint32_t)(top >> 4);
+                    s.fillp[k] = top + need > pool ? 0xFFFFu : (uint32_t)(top >> 4);
                     top += need;
                 }
+                s.scan_tmp[wave + 1] = nbig;
                 s.hdr->bcast = wave + 1;
             }
             g.sync();
             const uint32_t nwaves = s.hdr->bcast;
             const uint32_t ngrow_cf = s.hdr->ngrow;  // complete: the closed-form pass ended at a barrier, no blossom has run yet
             g.sync();
-            uint32_t k0 = 0;
             for (uint32_t wave = 0; wave < nwaves; wave++) {
-                uint32_t k1 = k0;
-                while (k1 < nbig && (s.fillp[k1] >> 16) == wave) k1++;
+                const uint32_t k0 = s.scan_tmp[wave], k1 = s.scan_tmp[wave + 1];
                 for (uint32_t k = k0 + g.warp; k < k1; k += g.nwarps) {
-                    const uint32_t off16 = s.fillp[k] & 0xFFFFu;
+                    const uint32_t off16 = s.fillp[k];
                     solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
                 }
                 // A warp without (further) blossoms in this wave serves the growth requests the closed forms made.
                 grow_some(s, g, ngrow_cf);
-                k0 = k1;
                 g.sync();
             }
             pt.lap(9);
@@ -2293,6 +2338,9 @@ template <class G>
 CB_HDN void paths_shot(Shot &s, const G &g) {
     for (uint32_t i = g.tid; i < s.M; i += g.n) s.path_len[i] = 0;
     g.sync();
+#ifdef CB_XPROF
+    unsigned long long xt = cb_clock();
+#endif
     // Pairs whose smaller event knows where the partner sits in its near-table row: one thread each.
     uint64_t wsum = 0;
     for (uint32_t i = (uint32_t)g.tid; i < s.M; i += (uint32_t)g.n) {
@@ -2308,18 +2356,24 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
     }
     if (wsum) cb_atomic_add64(&s.hdr->weight, wsum);
     g.sync();
+    CB_XLAP(s, g, xt, 14)
     // The rest (seen only from the partner's side, or found by a search): one warp each.
     wsum = 0;
-    for (uint32_t i = g.warp; i < s.M; i += g.nwarps) {
-        int32_t j = s.partner[i];
-        if (j > (int32_t)i && s.path_len[i] == 0) {
-            int64_t d = seen_distance(s, i, (uint32_t)j);
+    for (uint32_t base = (uint32_t)g.warp * (uint32_t)g.lanes; base < s.M; base += (uint32_t)(g.nwarps * g.lanes)) {
+        const uint32_t mine = base + (uint32_t)g.lane;  // the lanes look at 32 events at a time
+        uint32_t todo = g.ballot(mine < s.M && s.partner[mine] > (int32_t)mine && s.path_len[mine] == 0);
+        while (todo) {
+            const uint32_t i = base + ctz32(todo);
+            todo &= todo - 1;
+            const uint32_t j = (uint32_t)s.partner[i];
+            int64_t d = seen_distance(s, i, j);
             wsum += (uint64_t)d;
-            extract_path(s, g, i, (uint32_t)j, d);
+            extract_path(s, g, i, j, d);
         }
     }
     if (wsum && g.lane == 0) cb_atomic_add64(&s.hdr->weight, wsum);
     g.sync();
+    CB_XLAP(s, g, xt, 15)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
