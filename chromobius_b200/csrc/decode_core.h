@@ -2341,18 +2341,49 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
 #ifdef CB_XPROF
     unsigned long long xt = cb_clock();
 #endif
-    // Pairs whose smaller event knows where the partner sits in its near-table row: one thread each.
+    // Pairs whose partner sits in the near-table row of the smaller event: one thread each.
     uint64_t wsum = 0;
     for (uint32_t i = (uint32_t)g.tid; i < s.M; i += (uint32_t)g.n) {
         const int32_t j = s.partner[i];
         if (j <= (int32_t)i) continue;
         const NbEntry *l = nb_list(s, i);
+        uint32_t pos = NO_INDEX;
+        int64_t d = -1;
         for (uint32_t k = 0; k < s.nb_cnt[i]; k++)
             if (l[k].ev == (uint32_t)j) {
-                if (l[k].pos != NO_INDEX && near_path_emit(s, i, s.event_node(i), s.event_node((uint32_t)j), l[k].pos, false))
-                    wsum += (uint64_t)l[k].d;
+                pos = l[k].pos;
+                d = l[k].d;
                 break;
             }
+        const uint32_t src = s.event_node(i), dst = s.event_node((uint32_t)j);
+        if (d < 0 && s.T.near_stride) {
+            // seen from the partner's side only: take the distance from there and look the partner up in this event's
+            // row (the canonical path is defined from the smaller event), four entries per step
+            const NbEntry *lj = nb_list(s, (uint32_t)j);
+            for (uint32_t k = 0; k < s.nb_cnt[j]; k++)
+                if (lj[k].ev == i) {
+                    d = lj[k].d;
+                    break;
+                }
+            for (uint32_t p = 0; d >= 0 && p < s.T.near_stride && pos == NO_INDEX; p += 4) {
+                const U4 pair0 = *(const U4 *)near_at(s.T, src, p);
+                const U4 pair1 = *(const U4 *)near_at(s.T, src, p + 2);
+                const NearEntry e[4] = {{pair0.x, pair0.y}, {pair0.z, pair0.w}, {pair1.x, pair1.y}, {pair1.z, pair1.w}};
+                bool past = false;
+                for (int k = 0; k < 4; k++) {
+                    if (e[k].dist_flag == NEAR_PAD || (int64_t)(e[k].dist_flag & 0x7FFFFFFFu) > d) {
+                        past = true;
+                        break;
+                    }
+                    if ((e[k].node_pred & 0xFFFFFFu) == dst && (int64_t)(e[k].dist_flag & 0x7FFFFFFFu) == d) {
+                        pos = p + (uint32_t)k;
+                        break;
+                    }
+                }
+                if (past) break;
+            }
+        }
+        if (pos != NO_INDEX && near_path_emit(s, i, src, dst, pos, false)) wsum += (uint64_t)d;
     }
     if (wsum) cb_atomic_add64(&s.hdr->weight, wsum);
     g.sync();

@@ -1011,8 +1011,8 @@ HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
         if (!t.ignored[d]) t.ingest_mask[d >> 3] |= (uint8_t)(1u << (d & 7));
     }
     if (near_stride == NEAR_STRIDE_AUTO) {
-        // as many entries per node as a 128 MB table holds: the hot part (first chunk of every row) stays far below that
-        const uint64_t budget = 128ull << 20;
+        // as many entries per node as a 256 MB table holds (HBM is plentiful; only the first chunks of the rows are hot)
+        const uint64_t budget = 256ull << 20;
         const uint64_t nodes = std::max<uint64_t>(uint64_t{t.num_dets} * 2, 1);
         near_stride = (uint32_t)std::min<uint64_t>(budget / (nodes * sizeof(NearEntry)) / 32 * 32, NEAR_MAX_STRIDE);
         if (const char *env = std::getenv("CB200_NEAR_STRIDE")) near_stride = (uint32_t)std::strtoul(env, nullptr, 10);
