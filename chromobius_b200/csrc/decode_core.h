@@ -1747,7 +1747,26 @@ CB_HDN bool solve_component_four(Shot &s, const uint32_t *mem) {
             best_cost = x + y;
         }
     }
-    if (best < 0) return false;
+    if (best < 0) {
+        // No pairing has both edges: the seen edges form a star (the only connected graph on four vertices without a
+        // perfect matching). The blossom's greedy start pairs the centre with its closest leaf (lowest index on ties) and
+        // no augmenting path exists afterwards, so the other two leaves are left over and look further.
+        int c = -1;
+        for (int a = 0; a < 4 && c < 0; a++) {
+            int deg = 0;
+            for (int b = 0; b < 4; b++) deg += d[a][b] >= 0;
+            if (deg == 3) c = a;
+        }
+        if (c < 0) return false;
+        int leaf = -1;
+        for (int b = 0; b < 4; b++)
+            if (b != c && (leaf < 0 || d[c][b] < d[c][leaf])) leaf = b;
+        for (int b = 0; b < 4; b++) {
+            s.solved[mem[b]] = 0;
+            if (b != c && b != leaf) request_growth(s, mem[b], -1);
+        }
+        return true;
+    }
     const int A = pa[best][0], B = pa[best][1], C = pa[best][2], D = pa[best][3];
     const int64_t dab = d[A][B], dcd = d[C][D];
     int64_t P = dab + dcd, Q = dab - dcd;
@@ -2133,7 +2152,10 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
             g.sync();
             for (uint32_t wave = 0; wave < nwaves; wave++) {
                 const uint32_t k0 = s.scan_tmp[wave], k1 = s.scan_tmp[wave + 1];
-                for (uint32_t k = k0 + g.warp; k < k1; k += g.nwarps) {
+                // largest first, dealt out in serpentine order (warp 0 gets the 1st and the 16th, warp 7 the 8th and 9th)
+                for (uint32_t base = k0, pass = 0; base < k1; base += g.nwarps, pass++) {
+                    const uint32_t k = base + ((pass & 1) ? (uint32_t)(g.nwarps - 1 - g.warp) : (uint32_t)g.warp);
+                    if (k >= k1) continue;
                     const uint32_t off16 = s.fillp[k];
                     solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
