@@ -233,6 +233,7 @@ def run_gpu(args):
     barrier()
     dev_ms = 0.0
     decode_kernel_ms = 0.0
+    coll_total_ms = 0.0
     launches = 0
     events = 0
     rounds = 0
@@ -244,12 +245,20 @@ def run_gpu(args):
             st, coll_ms, mistakes = device_step()
             dev_ms += st.ms_total + coll_ms
             decode_kernel_ms += st.ms_decode
+            coll_total_ms += coll_ms
             launches += st.kernel_launches + 4  # + the elementwise/reduction kernels of collectives() (torch)
             events += st.num_detection_events
             rounds += st.matcher_rounds
             retried += st.num_retried_shots
         barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
+    # per-rank split (diagnostic): library time per step and time inside the collectives, which includes waiting for
+    # the slowest rank to arrive
+    mine = torch.tensor([(dev_ms - coll_total_ms) / args.steps, coll_total_ms / args.steps], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(x[0]), 2), round(float(x[1]), 2)] for x in per_rank]
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,6 +321,7 @@ def run_gpu(args):
                        'retried_shots_per_step': retried / args.steps, 'group_threads': group_threads,
                        'mistakes_last_step_all_gpus': mistakes, 'decoder_compile_s': compile_s,
                        'decoder_table_bytes': dec.table_bytes, 'wall_ms_per_step': wall_ms / args.steps,
+                       'per_rank_ms_per_step_decode_and_collectives': per_rank,
                        'timing': 'CUDA events on the library stream (per call) + torch events for the collectives, max over ranks'},
             'e2e': {'value': e2e_value, 'unit': 'shots/s', 'h2d_bytes_per_step': E * nb, 'd2h_bytes_per_step': E * ob,
                     'shots_per_gpu_per_step': E, 'matches_device_path': e2e_ok},

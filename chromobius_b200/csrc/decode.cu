@@ -410,7 +410,14 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     pl.cfg.sh_found = 16;
     pl.cfg.ht_log2 = gl;
     pl.cfg.found_cap = 256u << (2 * escalation);
-    pl.cfg.max_events = std::max<uint32_t>(2 * max_det_events, 2);
+    // Event capacity in coarse steps, and sticky: a batch that fits the layout the arena already has keeps it, so a
+    // stream of batches with slightly different maxima does not re-allocate and re-initialise the arena per call.
+    pl.cfg.max_events = (std::max<uint32_t>(2 * max_det_events, 2) + 127u) & ~127u;
+    {
+        const cb200_decoder::ArenaState &prev = d->arenas[std::min<uint32_t>(escalation, 3)];
+        if (prev.group == group && prev.cfg.max_events >= pl.cfg.max_events && prev.cfg.max_events / 2 <= pl.cfg.max_events)
+            pl.cfg.max_events = prev.cfg.max_events;
+    }
     pl.cfg.dyn_bytes = ((uint64_t)(64 << 10) + (uint64_t)3072 * pl.cfg.max_events) << (3 * escalation);
     uint32_t nwarps = group == 32 ? 1 : group / 32;
     pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
