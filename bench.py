@@ -5,8 +5,12 @@
     python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle on the box's host cores (reference arm)
 
 A step = one pass of the decode path over one batch of `--shots` synthetic shots per GPU (weak scaling: every GPU holds a
-replica of the decoder tables and its own batch). Shots are drawn on the device by the DEM sampler (independent
-mechanisms of the midout_color_code_d25_r100_p1000 detector error model); the batch is larger than L2.
+replica of the decoder tables and its own batch). The default, 1 250 000 shots per GPU per step, is one GPU's share of
+BASELINE.json's headline configuration (10 M shots sharded across 8 B200), so `--gpus 8` is exactly that configuration.
+Shots are drawn on the device by the DEM sampler (independent mechanisms of the midout_color_code_d25_r100_p1000
+detector error model); the batch (3.85 GB per GPU) is far larger than L2. The batch size matters: per-shot decode time
+has a long tail (mean 1.5 ms, the longest shot of 65 536 takes 60-100 ms), and the persistent kernel ends when its
+last shot does -- a 65 536-shot batch loses ~15 % to that tail (`--shots 65536` reproduces the earlier rounds' figure).
 
   value : shots/s with the batch already resident in HBM, timed with the CUDA events the library records on its own
           stream (sum over the K steps, max over ranks).
@@ -52,28 +56,31 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self.stop = threading.Event()
-        self.thread = None
-
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        # ONE long-lived nvidia-smi per rank (-lms 200), as in the recipe: spawning a fresh nvidia-smi per sample costs
+        # about a CPU-second each on an 8-GPU box and starves the ranks' launch threads.
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.thread.join(timeout=6)
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        for ln in (out or '').splitlines():
+            if ln.strip():
+                self.rows.append([x.strip() for x in ln.split(',')])
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
@@ -267,7 +274,7 @@ def run_gpu(args):
     group_threads = st.group_threads
 
     # ---- e2e: public API, pinned host input, host output ----
-    E = min(args.e2e_shots, S)
+    E = min(args.e2e_shots, S) if args.e2e_shots > 0 else S
     h_dets_t = torch.empty((E, nb), dtype=torch.uint8).pin_memory()
     h_dets_t.copy_(d_dets[:E])
     h_dets = h_dets_t.numpy()
@@ -293,7 +300,9 @@ def run_gpu(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, 'profiles', 'decode_kernel_traffic.json')) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                tj = json.load(f)
+            # the ncu capture is taken at a smaller launch (ncu replays the kernel ~40 times): scaled to this launch's shots
+            traffic = tj['dram_bytes_per_launch'] * S / tj.get('shots_per_launch', 65536)
         except Exception:
             pass
         cores = host_cores()
@@ -317,6 +326,7 @@ def run_gpu(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
             'config': {'workload': args.workload, 'shots_per_gpu_per_step': S, 'input_bytes_per_gpu_per_step': S * nb,
                        'l2_policy': 'inputs larger than L2 (%d MB per step vs 126 MB L2)' % (S * nb // 1000000),
+                       'traffic_source': 'ncu --set full capture at 65536 shots per launch, scaled by shots (profiles/decode_kernel_traffic.json)',
                        'detection_events_per_shot': events / (args.steps * S), 'matcher_rounds_per_shot': rounds / (args.steps * S),
                        'retried_shots_per_step': retried / args.steps, 'group_threads': group_threads,
                        'mistakes_last_step_all_gpus': mistakes, 'decoder_compile_s': compile_s,
@@ -346,8 +356,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default=WORKLOAD)
-    ap.add_argument('--shots', type=int, default=65536, help='shots per GPU per step')
-    ap.add_argument('--e2e-shots', type=int, default=65536)
+    ap.add_argument('--shots', type=int, default=1250000, help='shots per GPU per step')
+    ap.add_argument('--e2e-shots', type=int, default=0, help='shots per GPU per e2e step (0 = --shots)')
     ap.add_argument('--cpu-shots-per-core', type=int, default=6144,
                     help='CPU legs: shots per host core per sample (~15 s at ~400 shots/s/core)')
     ap.add_argument('--group', type=int, default=0)

@@ -167,6 +167,15 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
     bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, cb_smem + (size_t)gib * smem_per_group, g);
     init_group_shared(s, g);
     const uint32_t total = p.shot_list ? p.list_len : p.num_shots;
+#ifdef CB_TAIL_PROF
+    // diagnostic build: slot 21 = first group's start (globaltimer ns), 20 = sum of group finish offsets, 22 = last finish
+    unsigned long long tail_t0 = 0;
+    if (p.phase_cycles && g.tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        atomicCAS(&p.phase_cycles[21], 0ull, now);
+    }
+#endif
     while (true) {
         if (g.tid == 0) s.hdr->bcast = atomicAdd(p.work_counter, 1u);
         g.sync();
@@ -175,7 +184,40 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
         if (k >= total) break;
         uint32_t shot = p.shot_list ? p.shot_list[k] : k;
         decode_shot(s, p, shot, g);
+        // Out of scratch: again, in a spare arena with the next level's scratch, if one is free (decode_shot ended with a
+        // barrier after thread 0 stored the status). Otherwise the host's retry launch takes the shot.
+        if (p.spare_arena && p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) {
+            if (g.tid == 0) {
+                uint32_t slot = NO_INDEX;
+                for (uint32_t c = 0; c < p.num_spares && slot == NO_INDEX; c++)
+                    if (atomicCAS(&p.spare_claim[c], 0u, 1u) == 0u) slot = c;
+                s.hdr->bcast = slot;
+            }
+            g.sync();
+            const uint32_t slot = s.hdr->bcast;
+            g.sync();
+            if (slot != NO_INDEX) {
+                uint8_t *const shared = cb_smem + (size_t)gib * smem_per_group;
+                bind_shot(s, p, p.spare_cfg, p.spare_arena + (uint64_t)slot * p.spare_stride, shared, g);
+                decode_shot(s, p, shot, g);
+                if (g.tid == 0) {
+                    __threadfence();
+                    atomicExch(&p.spare_claim[slot], 0u);
+                    atomicAdd(p.spare_retries, 1u);
+                }
+                bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, shared, g);
+            }
+        }
     }
+#ifdef CB_TAIL_PROF
+    if (p.phase_cycles && g.tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        tail_t0 = *(volatile unsigned long long *)&p.phase_cycles[21];
+        atomicAdd(&p.phase_cycles[20], now - tail_t0);
+        atomicMax(&p.phase_cycles[22], now - tail_t0);
+    }
+#endif
 }
 
 // K3: u64 masks -> little-endian observable bytes, integer weights -> float32 (decode/pymatcher.cc:40).
@@ -233,7 +275,7 @@ struct cb200_decoder {
     } arenas[4];  // one cached arena per escalation level, so retry passes do not evict the main layout
     DeviceBuf<uint64_t> d_obs64;
     DeviceBuf<int64_t> d_wint, d_wint_out, d_edges;
-    DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list;
+    DeviceBuf<uint32_t> d_status, d_rounds, d_counts, d_scalars, d_list, d_spare_claim;
     DeviceBuf<unsigned long long> d_phase;
     bool profile_phases = false;
     unsigned long long phase_cycles[24] = {};
@@ -419,6 +461,10 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
             pl.cfg.max_events = prev.cfg.max_events;
     }
     pl.cfg.dyn_bytes = ((uint64_t)(64 << 10) + (uint64_t)3072 * pl.cfg.max_events) << (3 * escalation);
+    // tests: a first-level scratch this many times too small, so that the retry paths (spare arenas, retry launch) run
+    if (escalation == 0)
+        if (const char *env = getenv("CB200_TEST_SCRATCH_DIV"))
+            pl.cfg.dyn_bytes = std::max<uint64_t>(4096, pl.cfg.dyn_bytes / std::max<uint64_t>(1, strtoull(env, nullptr, 10)));
     uint32_t nwarps = group == 32 ? 1 : group / 32;
     pl.smem_per_group = (uint32_t)shared_bytes_per_group(pl.cfg, d->dview.num_dets, nwarps);
     auto occupancy = [&](uint32_t smem) {
@@ -553,11 +599,34 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         uint64_t items = esc == 0 ? n : retry.size();
         Plan pl = make_plan(d, items, max_count, (double)total_events / (double)n, esc);
         ensure_arena(d, pl, p, launches, esc);
+        p.spare_arena = nullptr;
+        p.num_spares = 0;
         if (esc == 0) {
             st.group_threads = pl.group;
             st.num_groups = pl.groups;
             p.shot_list = nullptr;
             p.list_len = 0;
+            // Spare arenas of the next escalation level for in-kernel retries (DecodeParams::spare_arena). They need the
+            // main plan's shared-memory layout; only worth it when the groups work through a queue of shots.
+            constexpr uint32_t NUM_SPARES = 16;
+            const bool no_spares = getenv("CB200_NO_SPARES") != nullptr;  // experiments / tests
+            if (!no_spares && n > pl.groups) {
+                Plan sp = make_plan(d, NUM_SPARES, max_count, (double)total_events / (double)n, 1);
+                if (sp.group == pl.group && sp.smem_per_group == pl.smem_per_group && sp.cfg.sh_ht_log2 == pl.cfg.sh_ht_log2 &&
+                    sp.cfg.sh_pool == pl.cfg.sh_pool && sp.cfg.sh_events == pl.cfg.sh_events && sp.cfg.sh_found == pl.cfg.sh_found &&
+                    sp.cfg.max_events >= pl.cfg.max_events) {
+                    DecodeParams q = p;
+                    ensure_arena(d, sp, q, launches, 1);
+                    d->d_spare_claim.ensure(NUM_SPARES);
+                    CUDA_CHECK(cudaMemsetAsync(d->d_spare_claim.ptr, 0, NUM_SPARES * 4, s));
+                    p.spare_arena = q.arena;
+                    p.spare_stride = q.arena_stride;
+                    p.spare_cfg = q.cfg;
+                    p.num_spares = std::min<uint32_t>(NUM_SPARES, sp.groups);
+                    p.spare_claim = d->d_spare_claim.ptr;
+                    p.spare_retries = d->d_scalars.ptr + 5;
+                }
+            }
         } else {
             d->d_list.ensure(retry.size());
             CUDA_CHECK(cudaMemcpyAsync(d->d_list.ptr, retry.data(), retry.size() * 4, cudaMemcpyHostToDevice, s));
@@ -574,7 +643,10 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         launches++;
         if (esc == 0) CUDA_CHECK(cudaEventRecord(d->ev[3], s));
         CUDA_CHECK(cudaMemcpyAsync(status.data(), d->d_status.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        uint32_t spare_retries = 0;
+        if (p.spare_arena) CUDA_CHECK(cudaMemcpyAsync(&spare_retries, d->d_scalars.ptr + 5, 4, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+        st.num_retried_shots += spare_retries;
         retry.clear();
         for (uint32_t k = 0; k < n; k++)
             if (status[k] == SHOT_SCRATCH_OVERFLOW) retry.push_back(k);
@@ -709,7 +781,7 @@ void cb200_free(cb200_decoder *d) {
     d->d_tables.release();
     d->d_dets.release(); d->d_obs_bytes.release(); for (auto &a : d->arenas) a.buf.release(); d->d_obs64.release(); d->d_wint.release();
     d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();
-    d->d_scalars.release(); d->d_list.release(); d->d_wfloat.release(); d->d_phase.release();
+    d->d_scalars.release(); d->d_list.release(); d->d_spare_claim.release(); d->d_wfloat.release(); d->d_phase.release();
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);

@@ -114,6 +114,15 @@ struct DecodeParams {
     uint64_t arena_stride;
     ScratchConfig cfg;
     uint32_t *work_counter;      // persistent-kernel shot queue
+    // A few spare arenas with larger scratch (the next escalation level's configuration, same shared-memory layout): a
+    // group whose shot ran out of scratch claims one and decodes the shot again right away, while the other groups
+    // carry on -- instead of a retry launch after the kernel, where the heaviest shots of the batch would run alone.
+    uint8_t *spare_arena;        // num_spares * spare_stride bytes (nullptr: none)
+    uint64_t spare_stride;
+    ScratchConfig spare_cfg;
+    uint32_t num_spares;
+    uint32_t *spare_claim;       // [num_spares] 0 = free
+    uint32_t *spare_retries;     // counter: shots decoded again in a spare arena
     // optional profiling: cycles spent by thread 0 of every group in
     // [0] ingest [1] first ball growth [2] component building [3] component solves [4] ball re-growth
     // [5] path extraction [6] Euler tours + discharge [7] shots
@@ -371,18 +380,18 @@ struct Shot {
 };
 
 template <class G>
-CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *shared, const G &g) {
+CB_HD void bind_shot(Shot &s, const DecodeParams &p, const ScratchConfig &cfg, uint8_t *arena, uint8_t *shared, const G &g) {
     s.T = p.T;
-    s.cfg = p.cfg;
+    s.cfg = cfg;
     uint8_t *q = arena;
     s.hdr = (GroupHeader *)q;
     q += align16(sizeof(GroupHeader));
     s.scan_tmp = (uint32_t *)q;
     q += align16(SCAN_TMP * 4);
-    uint64_t gb = ball_table_bytes(p.cfg.ht_log2, p.cfg.found_cap);
-    bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp * gb, p.cfg.ht_log2, p.cfg.found_cap);
+    uint64_t gb = ball_table_bytes(cfg.ht_log2, cfg.found_cap);
+    bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp * gb, cfg.ht_log2, cfg.found_cap);
     q += (uint64_t)g.nwarps * gb;
-    uint64_t m = p.cfg.max_events;
+    uint64_t m = cfg.max_events;
     s.evdet = (uint32_t *)q; q += align16(m * 4);
     s.R = (int64_t *)q; q += align16(m * 8);
     s.h = (int64_t *)q; q += align16(m * 8);
@@ -400,7 +409,7 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     s.comp_dirty = q; q += align16(m);
     s.used_flag = q; q += align16(m);
     s.dyn = q;
-    s.dyn_cap = align16(p.cfg.dyn_bytes);
+    s.dyn_cap = align16(cfg.dyn_bytes);
     s.prof = p.phase_cycles;
     s.chunk_off = 0;
     s.chunk_left = 0;
@@ -410,28 +419,33 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
     uint8_t *sh = shared;
     s.words = (uint32_t *)sh; sh += align16(uint64_t{s.nwords} * 4);
     s.word_rank = (uint32_t *)sh; sh += align16((uint64_t{s.nwords} + 1) * 4);
-    uint64_t sb = ball_table_bytes(p.cfg.sh_ht_log2, p.cfg.sh_found);
-    bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, p.cfg.sh_ht_log2, p.cfg.sh_found);
+    uint64_t sb = ball_table_bytes(cfg.sh_ht_log2, cfg.sh_found);
+    bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, cfg.sh_ht_log2, cfg.sh_found);
     s.sh_tables = sh;
     s.sh_tables_bytes = (uint64_t)g.nwarps * sb;
-    if (align16(p.cfg.sh_pool) > s.sh_tables_bytes) s.sh_tables_bytes = align16(p.cfg.sh_pool);
+    if (align16(cfg.sh_pool) > s.sh_tables_bytes) s.sh_tables_bytes = align16(cfg.sh_pool);
     // hot per-event arrays in shared memory (every pass of a matcher round re-reads them right after other threads of
     // the group wrote them, which always misses L1)
     sh += s.sh_tables_bytes;
-    if (p.cfg.sh_events & 1) {
+    if (cfg.sh_events & 1) {
         s.uf = (uint32_t *)sh; sh += align16(m * 4);
         s.root = (uint32_t *)sh; sh += align16(m * 4);
     }
-    if (p.cfg.sh_events & 2) {
+    if (cfg.sh_events & 2) {
         s.pc = (uint32_t *)sh; sh += align16(m * 4);
         s.solved = sh; sh += align16(m);
         s.regrown = sh; sh += align16(m);
         s.stale = sh; sh += align16(m);
         s.comp_dirty = sh; sh += align16(m);
     }
-    if (p.cfg.sh_events & 4) {
+    if (cfg.sh_events & 4) {
         s.h = (int64_t *)sh; sh += align16(m * 8);
     }
+}
+
+template <class G>
+CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *shared, const G &g) {
+    bind_shot(s, p, p.cfg, arena, shared, g);
 }
 
 // Called once per group before the first shot of a launch (shared memory does not survive launches).
@@ -769,12 +783,14 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     }
     t.nused = nused;
     t.nfront = nfront;
+#ifndef CB_TAIL_PROF
     if (s.prof && lane == 0) {
         cb_atomic_add64((uint64_t *)&s.prof[19], prof_pops);
         cb_atomic_add64((uint64_t *)&s.prof[20], cb_clock() - prof_t0);
         cb_atomic_add64((uint64_t *)&s.prof[21], 1);
         cb_atomic_add64((uint64_t *)&s.prof[22], nused);
     }
+#endif
     if (result == BALL_OK && limit < 0) result = BALL_EXHAUSTED;
     *limit_out = limit;
     *nfound_out = nfound;
@@ -884,7 +900,9 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
         s.nb_off[i] = (uint32_t)((off - 1) >> 4);
         s.nb_cnt[i] = nfound;
         s.R[i] = limit;
+#ifndef CB_TAIL_PROF
         if (s.prof) cb_atomic_add64((uint64_t *)&s.prof[23], 1);
+#endif
     }
     g.wsync();
     return true;
@@ -1999,6 +2017,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
         s.cnt[i] = 0;
     }
     if (g.tid == 0) s.hdr->ncomp = 0;
+#ifdef CB_TAIL_PROF
+    if (g.tid == 0) s.hdr->pad_hdr[0] = 0;  // largest component of the shot (diagnostic build)
+#endif
     g.sync();
 #ifdef CB_XPROF
     unsigned long long xt = cb_clock();
@@ -2084,6 +2105,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                 s.comp_root[slot] = i;
                 s.start[i] = cb_atomic_add(&s.hdr->mem_top, s.cnt[i]);
                 s.fillp[i] = 0;
+#ifdef CB_TAIL_PROF
+                cb_atomic_max(&s.hdr->pad_hdr[0], s.cnt[i]);
+#endif
             }
         }
         g.sync();
@@ -2160,8 +2184,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PhaseTimer &pt) {
                     solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
                     g.wsync();
                 }
-                // A warp without (further) blossoms in this wave serves the growth requests the closed forms made.
-                grow_some(s, g, ngrow_cf);
+                // A warp without (further) blossoms in this wave serves the growth requests the closed forms made (not
+                // when the pool doubles as the warps' shared ball tables, i.e. without a near table).
+                if (!s.sh_ball.H) grow_some(s, g, ngrow_cf);
                 g.sync();
             }
             pt.lap(9);
@@ -2842,11 +2867,26 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
             for (int k = 0; k < 7; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[k], pt.t[k]);
             cb_atomic_add64((uint64_t *)&p.phase_cycles[7], 1);
             for (int k = 8; k < 11; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[8 + k], pt.t[k]);
+#if defined(CB_TAIL_PROF) && defined(__CUDA_ARCH__)
+            // diagnostic build: slot 19 = longest shot (cycles), slot 23 = shots longer than 8 M cycles (~4 ms)
+            unsigned long long tot_ = 0;
+            for (int k = 0; k < 7; k++) tot_ += pt.t[k];
+            atomicMax((unsigned long long *)&p.phase_cycles[19], tot_);
+            if (tot_ > 8000000ull) cb_atomic_add64((uint64_t *)&p.phase_cycles[23], 1);
+#endif
         }
         uint32_t st = s.hdr->status;
         p.status_out[shot] = st;
         p.obs_out[shot] = st ? 0 : s.hdr->obs;
         if (p.weight_out) p.weight_out[shot] = st ? 0 : (int64_t)s.hdr->weight;
+#if defined(CB_TAIL_PROF) && defined(__CUDA_ARCH__)
+        if (p.weight_out && p.phase_cycles) {  // diagnostic build: (cycles >> 10) | largest component << 32 | rounds << 56
+            unsigned long long tot_ = 0;
+            for (int k = 0; k < 7; k++) tot_ += pt.t[k];
+            p.weight_out[shot] = (int64_t)(((tot_ >> 10) & 0xFFFFFFFFull) | ((unsigned long long)(s.hdr->pad_hdr[0] & 0xFFFFFFu) << 32) |
+                                           ((unsigned long long)(rounds & 0x7Fu) << 56));
+        }
+#endif
         if (p.rounds_out) p.rounds_out[shot] = rounds;
     }
     g.sync();

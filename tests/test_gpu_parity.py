@@ -69,3 +69,34 @@ def test_lift_of_gpu_edges_matches_oracle_lift(libs, name):
         assert od.lift_edges(row, edges) == obs
         _, o_obs, o_w = od.decode_edges(row)
         assert o_w == w
+
+
+@pytest.mark.parametrize('name,shots,group', [('midout_color_code_d9_r36_p1000', 6000, 128),
+                                              ('midout_color_code_d9_r36_p1000', 3000, 256),
+                                              ('superdense_color_code_d5_r20_p1000', 6000, 32)])
+def test_out_of_scratch_retries_give_the_same_answers(libs, monkeypatch, name, shots, group):
+    """A shot that runs out of scratch is decoded again with larger scratch: inside the kernel in a spare arena, or, when
+    none is free (or CB200_NO_SPARES), by a retry launch. Both must return what a roomy first attempt returns."""
+    cb, oracle = libs
+    text = read_dem(name)
+    dets, _ = NumpyDemSampler(text).sample(shots, 5)
+    dec = cb._compile_text(text, device=0)
+    dec.set_tuning(group_threads=group)
+    pred0, w0 = dec.decode_with_integer_weights(dets)
+    assert dec.last_stats.num_retried_shots == 0
+    results = {}
+    for spares in (True, False):
+        monkeypatch.setenv('CB200_TEST_SCRATCH_DIV', '64')
+        if not spares:
+            monkeypatch.setenv('CB200_NO_SPARES', '1')
+        dec2 = cb._compile_text(text, device=0)
+        dec2.set_tuning(group_threads=group)
+        pred, w = dec2.decode_with_integer_weights(dets)
+        st = dec2.last_stats
+        monkeypatch.delenv('CB200_TEST_SCRATCH_DIV')
+        monkeypatch.delenv('CB200_NO_SPARES', raising=False)
+        assert st.num_retried_shots > 0, 'the test did not exercise the retry path'
+        assert st.num_failed_shots == 0
+        assert (w == w0).all() and (pred == pred0).all()
+        results[spares] = st.num_retried_shots
+    assert results[True] > 0 and results[False] > 0

@@ -1,13 +1,14 @@
 #!/usr/bin/env python3
 """Turns one `ncu --set full` capture of the decode kernel into the summary kept under profiles/.
 
-usage: ncu_summary.py report.ncu-rep out.txt traffic.json "free-text description of the capture"
+usage: ncu_summary.py report.ncu-rep out.txt traffic.json "free-text description of the capture" [shots per launch]
   out.txt      : selected raw metrics + stall samples / instructions by source function and line (tools/ncu_funcs.py)
   traffic.json : {"dram_bytes_per_launch": dram__bytes_read.sum + dram__bytes_write.sum, ...} read by bench.py
 """
 import csv, io, json, os, subprocess, sys
 
 rep, out_txt, out_json, desc = sys.argv[1:5]
+shots_per_launch = int(sys.argv[5]) if len(sys.argv) > 5 else 65536
 HERE = os.path.dirname(os.path.abspath(__file__))
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -44,6 +45,6 @@ with open(out_txt, 'w') as f:
     f.write(funcs)
 dram = to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
 with open(out_json, 'w') as f:
-    json.dump({'dram_bytes_per_launch': dram, 'kernel': kernel, 'capture': desc,
+    json.dump({'dram_bytes_per_launch': dram, 'shots_per_launch': shots_per_launch, 'kernel': kernel, 'capture': desc,
                'gpu_time_ms_under_ncu': float(metric['gpu__time_duration.sum'][0]) * {'ns': 1e-6, 'us': 1e-3, 'ms': 1, 's': 1e3}.get(metric['gpu__time_duration.sum'][1], 1)}, f, indent=1)
 print(open(out_txt).read()[:3000])
