@@ -18,7 +18,7 @@ d_pred = torch.empty((S, ob), dtype=torch.uint8, device=dev)
 d_w = torch.empty(S, dtype=torch.int64, device=dev)
 smp.sample_device(S, d_dets.data_ptr(), nb, d_actual.data_ptr(), seed=1000)
 torch.cuda.synchronize()
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", 3))):
     st = dec.decode_device(d_dets.data_ptr(), S, nb, d_pred.data_ptr(), weight_int_ptr=d_w.data_ptr())
     print('rep %d: total %.1f ms = h2d %.1f + count %.1f + decode(first launch) %.1f + d2h/finish %.1f + rest (retries, host) %.1f; retried %d, max events/shot %d, launches %d' % (
         rep, st.ms_total, st.ms_h2d, st.ms_count, st.ms_decode, st.ms_d2h,
