@@ -133,3 +133,42 @@ def test_device_resident_api_matches_host_api(libs):
     assert st.kernel_launches >= 3
     host_pred, host_w = dec.decode_with_integer_weights(d_dets.cpu().numpy())
     assert (d_pred.cpu().numpy() == host_pred).all() and (d_w.cpu().numpy() == host_w).all()
+
+
+def test_one_gpu_share_of_the_headline_config_with_and_without_spare_arenas(libs, monkeypatch):
+    """bench.py's step: 1.25 M shots of midout d25 r100 resident in HBM (one GPU's share of the 10 M-shot configuration).
+    The few shots of such a batch that run out of first-level scratch -- the heaviest ones -- must decode to the same
+    weights and predictions whether the kernel retries them in a spare arena or a retry launch does; and the
+    oracle agrees on those very shots."""
+    import torch
+    cb, oracle = libs
+    name, S = 'midout_color_code_d25_r100_p1000', 1250000
+    text = read_dem(name)
+    dec = cb._compile_text(text, device=0)
+    smp = cb.DeviceDemSampler(text, device=0)
+    nb, ob = dec.num_detector_bytes, dec.num_observable_bytes
+    dev = torch.device('cuda', 0)
+    d_dets = torch.empty((S, nb), dtype=torch.uint8, device=dev)
+    d_actual = torch.empty(S, dtype=torch.int64, device=dev)
+    smp.sample_device(S, d_dets.data_ptr(), nb, d_actual.data_ptr(), seed=1000)
+    torch.cuda.synchronize()
+    out = {}
+    for spares in (True, False):
+        if not spares:
+            monkeypatch.setenv('CB200_NO_SPARES', '1')
+        d_pred = torch.empty((S, ob), dtype=torch.uint8, device=dev)
+        d_w = torch.empty(S, dtype=torch.int64, device=dev)
+        st = dec.decode_device(d_dets.data_ptr(), S, nb, d_pred.data_ptr(), weight_int_ptr=d_w.data_ptr())
+        monkeypatch.delenv('CB200_NO_SPARES', raising=False)
+        assert st.num_failed_shots == 0
+        out[spares] = (d_pred, d_w, st.num_retried_shots, st.kernel_launches)
+    assert out[True][2] > 0 and out[True][2] == out[False][2], 'this batch is known to hold shots that need the second scratch level'
+    assert bool((out[True][0] == out[False][0]).all()) and bool((out[True][1] == out[False][1]).all())
+    # the heaviest shots (largest weights) against the oracle
+    w = out[True][1]
+    top = torch.topk(w, 12).indices.cpu().numpy()
+    rows = d_dets[torch.from_numpy(top).to(dev)].cpu().numpy()
+    o_obs, o_w = oracle.OracleDecoder(text).decode_batch(rows)
+    assert (o_w == w.cpu().numpy()[top]).all()
+    mistakes = int((out[True][0][:, 0].to(torch.int64) != d_actual).sum().item())
+    assert mistakes < 60  # logical error rate of this configuration is ~2.5e-6
