@@ -1854,7 +1854,9 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
 // run-time sized layout beyond.
 template <class G>
 CB_HD uint64_t blossom_bytes(uint32_t n) {
+#ifndef CB_NO_CAP8
     if (n <= 8) return Blossom<G, 8>::bytes_needed((int)n);
+#endif
     if (n <= 16) return Blossom<G, 16>::bytes_needed((int)n);
     if (n <= 32) return Blossom<G, 32>::bytes_needed((int)n);
     return Blossom<G, 0>::bytes_needed((int)n);
@@ -1969,8 +1971,11 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
 template <class G>
 CB_HD void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
     const uint32_t n = s.cnt[s.comp_root[c]];
+#ifndef CB_NO_CAP8
     if (scratch && n <= 8) solve_component_blossom_t<G, 8>(s, g, c, scratch);
-    else if (scratch && n <= 16) solve_component_blossom_t<G, 16>(s, g, c, scratch);
+    else
+#endif
+    if (scratch && n <= 16) solve_component_blossom_t<G, 16>(s, g, c, scratch);
     else if (scratch && n <= 32) solve_component_blossom_t<G, 32>(s, g, c, scratch);
     else solve_component_blossom_t<G, 0>(s, g, c, scratch);
 }
