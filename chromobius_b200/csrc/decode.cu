@@ -8,6 +8,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/chromobius_b200.h"
@@ -156,11 +157,13 @@ __global__ void __launch_bounds__(256) k_count_events(const uint8_t *__restrict_
 #ifndef CB_MIN_BLOCKS_256
 #define CB_MIN_BLOCKS_256 3
 #endif
-template <int GROUP>
+// PROF: launches of a call with phase profiling enabled keep the cycle counters (PhaseTimer); all others compile them out.
+template <int GROUP, bool PROF = false>
 __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP == 512 ? 2 : (GROUP == 256 ? CB_MIN_BLOCKS_256 : (GROUP == 192 ? 4 : 6)))
     k_decode(DecodeParams p, uint32_t num_groups, uint32_t smem_per_group) {
     uint32_t group, gib;
     DevGroup<GROUP> g;
+    typedef typename std::conditional<PROF, PhaseTimer, NullTimer>::type Timer;
     group_ids<GROUP>(group, gib, g);
     if (group >= num_groups) return;
     Shot s;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
         g.sync();
         if (k >= total) break;
         uint32_t shot = p.shot_list ? p.shot_list[k] : k;
-        decode_shot(s, p, shot, g);
+        decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
         // Out of scratch: again, in a spare arena with the next level's scratch, if one is free (decode_shot ended with a
         // barrier after thread 0 stored the status). Otherwise the host's retry launch takes the shot.
         if (p.spare_arena && p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) {
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
             if (slot != NO_INDEX) {
                 uint8_t *const shared = cb_smem + (size_t)gib * smem_per_group;
                 bind_shot(s, p, p.spare_cfg, p.spare_arena + (uint64_t)slot * p.spare_stride, shared, g);
-                decode_shot(s, p, shot, g);
+                decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
                 if (g.tid == 0) {
                     __threadfence();
                     atomicExch(&p.spare_claim[slot], 0u);
@@ -389,7 +392,12 @@ void launch_decode(const DecodeParams &p, uint32_t groups, uint32_t smem_per_gro
         if (pct >= 0) cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
         cudaGetLastError();
     }
-    k_decode<GROUP><<<blocks, threads, smem, st>>>(p, groups, smem_per_group);
+    if (p.phase_cycles) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_decode<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_decode<GROUP, true><<<blocks, threads, smem, st>>>(p, groups, smem_per_group);
+    } else {
+        k_decode<GROUP><<<blocks, threads, smem, st>>>(p, groups, smem_per_group);
+    }
 }
 template <int GROUP>
 int blocks_per_sm(size_t smem_per_group) {
