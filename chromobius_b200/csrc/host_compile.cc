@@ -295,10 +295,85 @@ struct AtomHash {
 };
 typedef std::unordered_map<Atom, uint64_t, AtomHash> AtomTable;
 
+// The order in which libstdc++'s std::unordered_map<uint32_t, T> (identity hash, maximum load factor 1, prime bucket
+// counts) iterates its keys after a sequence of first-time insertions. The reference's charge graph is such a container
+// (graph/charge_graph.h:52) and its two-step path search returns the first path met while iterating it
+// (graph/drag_graph.cc:87), so this order decides 1-17 % of the predictions on some circuits. It is restated here, not
+// taken from the platform's <unordered_map>, so the tables do not depend on the standard library the product is built
+// with; tests/test_decode_path_cpu.py checks it against the real container (which the oracle uses).
+//   - an element whose bucket is empty becomes the head of the whole list; otherwise it goes to the front of its bucket;
+//   - growth happens before an insertion that would exceed the bucket count: 1 -> 13 -> 29 -> 59 -> 127 -> ... (the
+//     smallest listed prime >= twice the old count), and re-buckets the elements in list order by the same rule.
+class StdHashOrder {
+    static constexpr int32_t NIL = -1, HEAD = -2;
+    std::vector<uint32_t> keys_;
+    std::vector<int32_t> next_;
+    std::vector<int32_t> before_{NIL};  // per bucket: the element its run follows (HEAD: the run starts the list), NIL: empty
+    int32_t head_ = NIL;
+    size_t next_resize_ = 0;
+
+    int32_t &link(int32_t prev) { return prev == HEAD ? head_ : next_[prev]; }
+    static size_t next_bucket_count(size_t at_least) {
+        static const size_t growth[] = {13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229, 172933,
+                                        351061, 712697, 1447153};
+        for (size_t c : growth)
+            if (c >= at_least) return c;
+        fail("charge graph node with more than a million neighbours");
+        return 0;
+    }
+    void place(int32_t i, std::vector<int32_t> &before, size_t &first_bucket, bool rehashing) {
+        size_t b = keys_[i] % before.size();
+        if (before[b] == NIL) {
+            next_[i] = head_;
+            head_ = i;
+            before[b] = HEAD;
+            if (next_[i] != NIL) before[rehashing ? first_bucket : keys_[next_[i]] % before.size()] = i;
+            first_bucket = b;
+        } else {
+            next_[i] = link(before[b]);
+            link(before[b]) = i;
+        }
+    }
+
+  public:
+    // `key` must not have been inserted before.
+    void insert_new(uint32_t key) {
+        size_t n = keys_.size();
+        if (n + 1 > next_resize_) {
+            size_t want = std::max<size_t>(n + 1, next_resize_ ? 0 : 11);
+            if (want >= before_.size()) {
+                size_t count = next_bucket_count(std::max(want + 1, before_.size() * 2));
+                std::vector<int32_t> before(count, NIL);
+                int32_t p = head_;
+                head_ = NIL;
+                size_t first_bucket = 0;
+                while (p != NIL) {
+                    int32_t nx = next_[p];
+                    place(p, before, first_bucket, true);
+                    p = nx;
+                }
+                before_.swap(before);
+                next_resize_ = count;
+            } else {
+                next_resize_ = before_.size();
+            }
+        }
+        keys_.push_back(key);
+        next_.push_back(NIL);
+        size_t unused = 0;
+        place((int32_t)n, before_, unused, false);
+    }
+    template <class F>
+    void for_each(F f) const {
+        for (int32_t p = head_; p != NIL; p = next_[p]) f(keys_[p]);
+    }
+};
+
 struct Ctx {
     const FlatDem &dem;
     HostTables &t;
     AtomTable atoms;
+    std::vector<StdHashOrder> charge_visit_order;  // per charge-graph node: the reference container's iteration order
     Ctx(const FlatDem &d, HostTables &tt) : dem(d), t(tt) {}
 
     uint8_t color_of(uint32_t d) const { return t.color[d]; }
@@ -593,16 +668,22 @@ void pass_rgb_reps(Ctx &cx, const std::vector<Atom> &order, const std::vector<ui
     }
 }
 
-// graph/charge_graph.cc:80-160. Per-node neighbour lists kept sorted; writes overwrite (last writer wins).
+// graph/charge_graph.cc:80-160. Per-node neighbour lists kept sorted; writes overwrite (last writer wins). The order in
+// which the reference's container would iterate each node's neighbours is tracked beside it (Ctx::charge_visit_order).
 void pass_charge_graph(Ctx &cx, const std::vector<Atom> &order, const std::vector<uint64_t> &obs) {
     auto &g = cx.t.charge_graph;
     g.assign(cx.t.num_dets, {});
+    cx.charge_visit_order.assign(cx.t.num_dets, {});
     auto put = [&](uint32_t at, uint32_t nb, uint64_t f) {
         auto &row = g[at];
         auto it = std::lower_bound(row.begin(), row.end(), std::make_pair(nb, (uint64_t)0),
                                    [](const auto &x, const auto &y) { return x.first < y.first; });
-        if (it != row.end() && it->first == nb) it->second = f;
-        else row.insert(it, {nb, f});
+        if (it != row.end() && it->first == nb) {
+            it->second = f;
+        } else {
+            row.insert(it, {nb, f});
+            cx.charge_visit_order[at].insert_new(nb);
+        }
     };
     auto link = [&](uint32_t a, uint32_t b, uint64_t f) {
         if (a != NONE) put(a, b, f);
@@ -648,9 +729,10 @@ void pass_charge_graph(Ctx &cx, const std::vector<Atom> &order, const std::vecto
     }
 }
 
-// graph/drag_graph.cc:24-105: obs flip of a path of at most 2 charge-graph edges.
-// The reference walks std::unordered_map buckets (unspecified order) and returns the first hit; we take neighbours in
-// descending id order (the mirror of its LIFO stack over an ascending insertion) and count disagreeing alternatives.
+// graph/drag_graph.cc:24-105 (BfsSearcher::find_shortest_path_obs_flip with max_cost = 2): obs flip of a path of at
+// most 2 charge-graph edges. The reference pushes src's neighbours in its container's iteration order (src itself
+// included through its self loop; the boundary is skipped), pops them from the back and returns the first one that has
+// dst as a neighbour. Searches whose answer depends on that order are counted in drag_ambiguities.
 bool short_path(Ctx &cx, uint32_t src, uint32_t dst, uint64_t &flip) {
     const auto &g = cx.t.charge_graph;
     if (src == dst) {
@@ -666,19 +748,22 @@ bool short_path(Ctx &cx, uint32_t src, uint32_t dst, uint64_t &flip) {
         return true;
     };
     if (find_in(src, dst, flip)) return true;
+    std::vector<uint32_t> level1;
+    cx.charge_visit_order[src].for_each([&](uint32_t nb) {
+        if (nb != NONE) level1.push_back(nb);
+    });
     bool found = false;
-    const auto &row = g[src];
-    for (size_t i = row.size(); i-- > 0;) {
-        if (row[i].first == NONE) continue;
-        uint64_t f2;
-        if (find_in(row[i].first, dst, f2)) {
-            uint64_t v = row[i].second ^ f2;
-            if (!found) {
-                found = true;
-                flip = v;
-            } else if (v != flip) {
-                cx.t.drag_ambiguities++;
-            }
+    for (size_t i = level1.size(); i-- > 0;) {
+        uint64_t f1 = 0, f2;
+        if (!find_in(level1[i], dst, f2)) continue;
+        find_in(src, level1[i], f1);
+        uint64_t v = f1 ^ f2;
+        if (!found) {
+            found = true;
+            flip = v;
+        } else if (v != flip) {
+            cx.t.drag_ambiguities++;
+            break;
         }
     }
     return found;
@@ -937,6 +1022,14 @@ void build_near_table(HostTables &t, uint32_t stride) {
     }
 }
 
+std::vector<uint32_t> reference_container_visit_order(const std::vector<uint32_t> &keys_in_insertion_order) {
+    StdHashOrder order;
+    for (uint32_t k : keys_in_insertion_order) order.insert_new(k);
+    std::vector<uint32_t> out;
+    order.for_each([&](uint32_t k) { out.push_back(k); });
+    return out;
+}
+
 HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
     HostTables t;
     if (dem.num_detectors > 0x7FFFFFFEull) fail("The detector error model is too large.");
@@ -1027,7 +1120,7 @@ HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
 // =================================================================================================
 namespace {
 constexpr uint64_t CACHE_MAGIC = 0x3030324253454c42ull;  // "BLESB200"
-constexpr uint64_t CACHE_VERSION = 3;
+constexpr uint64_t CACHE_VERSION = 4;  // 4: drag table follows the reference container's visit order
 
 struct Writer {
     FILE *f;
@@ -1197,7 +1290,10 @@ std::string HostTables::mobius_dem_text() const {
         }
         out += "\n";
     }
-    if (num_dets > 0) {
+    // decoder.cc:48-52: padded with a detector declaration when the errors do not mention the last Moebius node.
+    uint32_t mentioned = 0;
+    for (uint32_t v : mobius_edges) mentioned = std::max(mentioned, v + 1);
+    if (mentioned < num_dets * 2) {
         snprintf(buf, sizeof(buf), "detector D%u\n", num_dets * 2 - 1);
         out += buf;
     }

@@ -97,6 +97,11 @@ struct HostTables {
 // NEAR_STRIDE_AUTO sizes it from a byte budget (environment CB200_NEAR_STRIDE overrides).
 constexpr uint32_t NEAR_STRIDE_AUTO = 0xFFFFFFFFu;
 HostTables compile_tables(const FlatDem &dem, uint32_t near_stride = NEAR_STRIDE_AUTO);
+
+// Test hook: the order in which the reference's charge-graph container (libstdc++ std::unordered_map<uint32_t, uint64_t>,
+// src/chromobius/graph/charge_graph.h:52) iterates distinct keys inserted in the given sequence, as restated by the
+// compile step (the drag-table search depends on it, src/chromobius/graph/drag_graph.cc:87).
+std::vector<uint32_t> reference_container_visit_order(const std::vector<uint32_t> &keys_in_insertion_order);
 // (Re)builds t.near for the given stride from t.row_ptr / t.adj (multi-threaded).
 void build_near_table(HostTables &t, uint32_t near_stride);
 

@@ -261,6 +261,8 @@ struct AtomKey {
     }
 };
 typedef std::map<AtomKey, obsmask> AtomMap;
+// charge_graph.h:37-53: adjacency as the reference's own container type (its iteration order matters, see short_path_flip).
+typedef std::vector<std::unordered_map<node_t, obsmask>> ChargeGraph;
 
 struct RgbRep {
     node_t rgb[3] = {BOUNDARY, BOUNDARY, BOUNDARY};
@@ -532,7 +534,7 @@ struct Tables {
     AtomMap atomic_errors;
     std::vector<MobiusError> mobius;
     std::vector<RgbRep> rgb_reps;
-    std::vector<std::map<node_t, obsmask>> charge_graph;  // neighbor -> obs flip (BOUNDARY key allowed)
+    ChargeGraph charge_graph;  // neighbor -> obs flip (BOUNDARY key allowed)
     std::map<std::array<uint32_t, 4>, obsmask> drag;      // {n1, n2, c1, c2}
     std::unordered_map<uint64_t, obsmask> drag_lookup;    // same content, hashed (filled after the map is complete)
     static uint64_t drag_key(uint32_t n1, uint32_t n2, uint32_t c1, uint32_t c2) {
@@ -584,8 +586,8 @@ static std::vector<RgbRep> choose_rgb_reps(const AtomMap &atoms, const std::vect
 }
 
 // charge_graph.cc:80-160
-static std::vector<std::map<node_t, obsmask>> build_charge_graph(const AtomMap &atoms, size_t num_nodes) {
-    std::vector<std::map<node_t, obsmask>> g(num_nodes);
+static ChargeGraph build_charge_graph(const AtomMap &atoms, size_t num_nodes) {
+    ChargeGraph g(num_nodes);
     auto add_edge = [&](node_t a, node_t b, obsmask f) {
         if (a != BOUNDARY) g[a][b] = f;
         if (b != BOUNDARY) g[b][a] = f;
@@ -627,28 +629,40 @@ static std::vector<std::map<node_t, obsmask>> build_charge_graph(const AtomMap &
     return g;
 }
 
-// drag_graph.cc:24-105. The reference iterates a std::unordered_map (implementation-defined order) and returns the
-// first <=2-edge path it meets. We iterate neighbours in ascending id, newest-level-first like the reference's stack,
-// and count the (src,dst) pairs for which two 2-edge paths disagree (Tables::drag_ambiguities).
-static std::optional<obsmask> short_path_flip(
-    const std::vector<std::map<node_t, obsmask>> &g, node_t src, node_t dst, uint64_t *ambiguities) {
+// drag_graph.cc:24-105 (BfsSearcher::find_shortest_path_obs_flip, max_cost = 2). The reference walks
+// `graph.nodes[n].neighbors`, a std::unordered_map<uint32_t, uint64_t> (charge_graph.h:52), and returns the FIRST path
+// of at most two edges it meets. Several two-edge paths with different observable masks exist on some circuits
+// (toric d12: 4000 searches, midout488 d9: 380, superdense d5: 180), so the container's iteration order decides 1-17 %
+// of the predictions there. ChargeGraph here IS that container (same key/value types, same insertion sequence, the
+// libstdc++ the reference's CI builds with), and the search below visits in the reference's order: level-1 nodes are
+// pushed in src's iteration order (src itself included through its self loop -- src is never tagged as seen) and
+// popped from the back; each popped node's neighbours are scanned in its own iteration order.
+// `ambiguities` additionally counts the searches whose answer depends on that order (diagnostic only).
+static std::optional<obsmask> short_path_flip(const ChargeGraph &g, node_t src, node_t dst, uint64_t *ambiguities) {
     if (src == dst) return obsmask{0};
     auto it = g[src].find(dst);
     if (it != g[src].end()) return it->second;
-    std::optional<obsmask> found;
-    // level-1 nodes in the order the reference would pop them (LIFO over insertion order)
     std::vector<std::pair<node_t, obsmask>> level1;
+    std::set<node_t> seen;
     for (const auto &[nb, f] : g[src]) {
+        if (nb == dst) return f;
         if (nb == BOUNDARY) continue;
+        if (!seen.insert(nb).second) continue;
         level1.push_back({nb, f});
     }
+    std::optional<obsmask> found;
     for (size_t i = level1.size(); i-- > 0;) {
         auto [n, pf] = level1[i];
-        auto f2 = g[n].find(dst);
-        if (f2 != g[n].end()) {
-            obsmask v = pf ^ f2->second;
-            if (!found.has_value()) found = v;
-            else if (*found != v) (*ambiguities)++;
+        for (const auto &[nb, f] : g[n]) {
+            if (nb == dst) {
+                obsmask v = pf ^ f;
+                if (!found.has_value()) found = v;
+                else if (*found != v) {
+                    (*ambiguities)++;
+                    return found;
+                }
+                break;
+            }
         }
     }
     return found;
@@ -1875,7 +1889,8 @@ static std::string describe(const Tables &t) {
     for (size_t k = 0; k < t.charge_graph.size(); k++) {
         out << "    ChargeGraphNode{.neighbors={";
         bool first = true;
-        for (const auto &[nb, f] : t.charge_graph[k]) {
+        std::map<node_t, obsmask> sorted_nbrs(t.charge_graph[k].begin(), t.charge_graph[k].end());  // charge_graph.cc:43 sorts
+        for (const auto &[nb, f] : sorted_nbrs) {
             if (!first) out << ", ";
             first = false;
             out << "{";
@@ -1911,6 +1926,11 @@ static std::string describe(const Tables &t) {
         }
         out << "\n";
     }
+    // decoder.cc:48-52: padded with a detector declaration when the errors do not mention the last Moebius node.
+    uint64_t mentioned = 0;
+    for (const auto &me : t.mobius)
+        for (const auto &e : me.edges) mentioned = std::max<uint64_t>(mentioned, (uint64_t)std::max(e.first, e.second) + 1);
+    if (mentioned < t.num_dets * 2) out << "detector D" << (t.num_dets * 2 - 1) << "\n";
     out << "\n}\n";
     return out.str();
 }

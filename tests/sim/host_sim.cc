@@ -5,6 +5,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../chromobius_b200/csrc/decode_core.h"
@@ -35,6 +36,21 @@ void *cbsim_compile(const char *dem_text) {
     }
 }
 void cbsim_free(void *h) { delete (Sim *)h; }
+
+// Visit order of n distinct keys inserted in sequence: the compile step's restatement (which = 0) or the real
+// std::unordered_map<uint32_t, uint64_t> of this toolchain's libstdc++ (which = 1), the container the reference uses.
+void cbsim_container_visit_order(const uint32_t *keys, uint64_t n, int which, uint32_t *out) {
+    std::vector<uint32_t> seq(keys, keys + n);
+    if (which == 0) {
+        auto order = reference_container_visit_order(seq);
+        memcpy(out, order.data(), n * 4);
+    } else {
+        std::unordered_map<uint32_t, uint64_t> m;
+        for (uint32_t k : seq) m[k] = k;
+        uint64_t i = 0;
+        for (const auto &kv : m) out[i++] = kv.first;
+    }
+}
 uint64_t cbsim_num_detectors(void *h) { return ((Sim *)h)->tables.num_dets; }
 uint64_t cbsim_num_observables(void *h) { return ((Sim *)h)->tables.num_obs; }
 double cbsim_normalising_constant(void *h) { return ((Sim *)h)->tables.normalising_constant; }
