@@ -98,6 +98,16 @@ def load_library():
     L.cb200_set_groups_per_sm.argtypes = [vp, u32]
     L.cb200_profile_phases.restype = ctypes.c_int
     L.cb200_profile_phases.argtypes = [vp, ctypes.c_int, vp]
+    L.cb200_compile_multi.restype = ctypes.c_int
+    L.cb200_compile_multi.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(vp)]
+    L.cb200_multi_free.argtypes = [vp]
+    L.cb200_multi_free.restype = None
+    L.cb200_multi_num_devices.restype = ctypes.c_int
+    L.cb200_multi_num_devices.argtypes = [vp]
+    L.cb200_multi_replica.restype = vp
+    L.cb200_multi_replica.argtypes = [vp, ctypes.c_int]
+    L.cb200_multi_decode_batch.restype = ctypes.c_int
+    L.cb200_multi_decode_batch.argtypes = [vp, vp, u64, u64, vp, vp, vp, ctypes.POINTER(BatchStats)]
     L.cb200_sampler_last_error.restype = ctypes.c_char_p
     L.cb200_sampler_create.restype = ctypes.c_int
     L.cb200_sampler_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
@@ -146,7 +156,9 @@ class CompiledDecoder:
     def from_dem(dem, *, device=None):
         """Compiles a decoder for a stim.DetectorErrorModel (pybind/chromobius.pybind.cc:32-47).
 
-        The DEM crosses the boundary as text (`str(dem)`), exactly as in the reference.
+        The DEM crosses the boundary as text (`str(dem)`), exactly as in the reference. `device`: a GPU index (default:
+        CHROMOBIUS_B200_DEVICE / LOCAL_RANK / 0), a list of indices, or 'all' -- the latter two return a decoder that
+        splits every batch over those GPUs (MultiGpuCompiledDecoder).
         """
         type_name = str(type(dem))
         if 'stim.' not in type_name or '.DetectorErrorModel' not in type_name:
@@ -154,6 +166,10 @@ class CompiledDecoder:
         return _compile_text(str(dem), device)
 
     # -- the hot path ------------------------------------------------------------------------------------------
+    def _decode_host(self, dets_ptr, num_shots, stride, obs_ptr, weight_ptr, weight_int_ptr, stats):
+        return self._L.cb200_decode_batch(self._h, dets_ptr, num_shots, stride, obs_ptr, weight_ptr, weight_int_ptr,
+                                          CB200_IO_HOST, ctypes.byref(stats))
+
     def _predict(self, dets, include_weight):
         # argument checks and messages follow pybind/chromobius.pybind.cc:49-93
         if not isinstance(dets, np.ndarray) or dets.dtype != np.uint8:
@@ -188,9 +204,8 @@ class CompiledDecoder:
         result = np.empty(out_shape, np.uint8)
         weights = np.empty(w_shape, np.float32) if include_weight else None
         stats = BatchStats()
-        rc = self._L.cb200_decode_batch(
-            self._h, dets.ctypes.data_as(ctypes.c_void_p), num_shots, stride, result.ctypes.data_as(ctypes.c_void_p),
-            weights.ctypes.data_as(ctypes.c_void_p) if include_weight else None, None, CB200_IO_HOST, ctypes.byref(stats))
+        rc = self._decode_host(dets.ctypes.data_as(ctypes.c_void_p), num_shots, stride, result.ctypes.data_as(ctypes.c_void_p),
+                               weights.ctypes.data_as(ctypes.c_void_p) if include_weight else None, None, stats)
         self.last_stats = stats
         if rc != 0:
             _raise_last(self._L)
@@ -238,9 +253,8 @@ class CompiledDecoder:
         result = np.empty((n, self.num_observable_bytes), np.uint8)
         wint = np.empty(n, np.int64)
         stats = BatchStats()
-        rc = self._L.cb200_decode_batch(self._h, dets.ctypes.data_as(ctypes.c_void_p), n, dets.shape[1],
-                                        result.ctypes.data_as(ctypes.c_void_p), None, wint.ctypes.data_as(ctypes.c_void_p),
-                                        CB200_IO_HOST, ctypes.byref(stats))
+        rc = self._decode_host(dets.ctypes.data_as(ctypes.c_void_p), n, dets.shape[1], result.ctypes.data_as(ctypes.c_void_p),
+                               None, wint.ctypes.data_as(ctypes.c_void_p), stats)
         self.last_stats = stats
         if rc != 0:
             _raise_last(self._L)
@@ -294,6 +308,43 @@ class CompiledDecoder:
         return int(self._L.cb200_table_bytes(self._h))
 
 
+class MultiGpuCompiledDecoder(CompiledDecoder):
+    """One decoder replicated over several GPUs of the box (cb200_compile_multi): the same two predict methods, one call,
+    the batch split into contiguous row ranges that the devices decode side by side. Host buffers only."""
+
+    def __init__(self, _multi_handle, _lib_ref):
+        self._m = _multi_handle
+        self.num_devices = int(_lib_ref.cb200_multi_num_devices(_multi_handle))
+        # the first replica answers the queries; it is owned by the multi handle (see __del__)
+        CompiledDecoder.__init__(self, ctypes.c_void_p(_lib_ref.cb200_multi_replica(_multi_handle, 0)), _lib_ref)
+
+    def __del__(self):
+        try:
+            if self._m:
+                self._L.cb200_multi_free(self._m)
+                self._m = None
+                self._h = None
+        except Exception:
+            pass
+
+    def _decode_host(self, dets_ptr, num_shots, stride, obs_ptr, weight_ptr, weight_int_ptr, stats):
+        return self._L.cb200_multi_decode_batch(self._m, dets_ptr, num_shots, stride, obs_ptr, weight_ptr, weight_int_ptr,
+                                                ctypes.byref(stats))
+
+    def decode_device(self, *a, **k):
+        raise ValueError('a multi-GPU decoder takes host buffers; use the per-device decoders for device-resident batches')
+
+    def decode_shot_edges(self, dets_row):
+        raise ValueError('decode_shot_edges is a single-GPU debugging hook')
+
+    def set_tuning(self, group_threads=0, ht_log2=0, groups_per_sm=0):
+        for k in range(self.num_devices):
+            h = ctypes.c_void_p(self._L.cb200_multi_replica(self._m, k))
+            if self._L.cb200_set_tuning(h, group_threads, ht_log2) != 0:
+                _raise_last(self._L)
+            self._L.cb200_set_groups_per_sm(h, groups_per_sm)
+
+
 def _default_device():
     for key in ('CHROMOBIUS_B200_DEVICE', 'LOCAL_RANK'):
         v = os.environ.get(key)
@@ -304,6 +355,16 @@ def _default_device():
 
 def _compile_text(dem_text, device=None):
     L = load_library()
+    if isinstance(device, (list, tuple)) or device == 'all':
+        devs = [] if device == 'all' else [int(d) for d in device]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        handle = ctypes.c_void_p()
+        rc = L.cb200_compile_multi(dem_text.encode('utf-8'), arr if devs else None, len(devs), ctypes.byref(handle))
+        if rc != 0:
+            if rc == -2:
+                raise RuntimeError(L.cb200_last_error().decode('utf-8', 'replace'))
+            _raise_last(L)
+        return MultiGpuCompiledDecoder(handle, L)
     handle = ctypes.c_void_p()
     rc = L.cb200_compile(dem_text.encode('utf-8'), _default_device() if device is None else int(device), ctypes.byref(handle))
     if rc != 0:

@@ -6,7 +6,8 @@
 // messages and return types. Differences, all behind the same signatures:
 //   * the serial loop over Decoder::decode_detection_events becomes ONE cb200_decode_batch call (CUDA, sm_100a);
 //   * the GIL is released while the GPU decodes;
-//   * `device=` (keyword only, optional) picks the GPU; the default follows CHROMOBIUS_B200_DEVICE / LOCAL_RANK / 0.
+//   * `device=` (keyword only, optional) picks the GPU -- an index, a list of indices or 'all' (the batch is then split
+//     over those GPUs inside the one call, cb200_compile_multi); the default follows CHROMOBIUS_B200_DEVICE / LOCAL_RANK / 0.
 // There is no CPU fallback: without a CUDA device compile_decoder_for_dem raises.
 //
 // Build (see __graft_entry__.build_pybind): g++ -shared $(python -m pybind11 --includes) ... -l:libchromobius_b200.so
@@ -46,27 +47,63 @@ int default_device() {
     return 0;
 }
 
+// `device`: None (default device), an int, a list / tuple of ints, or 'all' (every visible GPU).
+struct DeviceSpec {
+    bool multi = false;
+    std::vector<int> devices;  // multi && empty: all
+};
+DeviceSpec device_spec_from(const py::object &device) {
+    DeviceSpec spec;
+    if (device.is_none()) {
+        spec.devices.push_back(default_device());
+    } else if (py::isinstance<py::str>(device)) {
+        if (py::cast<std::string>(device) != "all") throw std::invalid_argument("device must be an int, a list of ints or 'all'");
+        spec.multi = true;
+    } else if (py::isinstance<py::list>(device) || py::isinstance<py::tuple>(device)) {
+        spec.multi = true;
+        for (auto item : device) spec.devices.push_back(py::cast<int>(item));
+        if (spec.devices.empty()) throw std::invalid_argument("device list must not be empty");
+    } else {
+        spec.devices.push_back(py::cast<int>(device));
+    }
+    return spec;
+}
+
+// Owns one decoder, or one decoder replicated over several GPUs (cb200_compile_multi).
 struct Handle {
-    cb200_decoder *dec = nullptr;
-    explicit Handle(const std::string &dem_text, int device) {
-        int rc = cb200_compile(dem_text.c_str(), device, &dec);
+    cb200_decoder *dec = nullptr;  // the decoder that answers queries (replica 0 of a multi handle)
+    cb200_multi *multi = nullptr;
+    Handle(const std::string &dem_text, const DeviceSpec &spec) {
+        int rc;
+        if (spec.multi) {
+            rc = cb200_compile_multi(dem_text.c_str(), spec.devices.empty() ? nullptr : spec.devices.data(), (int)spec.devices.size(), &multi);
+            if (rc == CB200_OK) dec = cb200_multi_replica(multi, 0);
+        } else {
+            rc = cb200_compile(dem_text.c_str(), spec.devices[0], &dec);
+        }
         if (rc != CB200_OK) raise_last(rc);
     }
     ~Handle() {
-        if (dec) cb200_free(dec);
+        if (multi) cb200_multi_free(multi);
+        else if (dec) cb200_free(dec);
     }
     Handle(const Handle &) = delete;
     Handle &operator=(const Handle &) = delete;
 };
 
-int device_from(const py::object &device) { return device.is_none() ? default_device() : py::cast<int>(device); }
+DeviceSpec default_spec() {
+    DeviceSpec spec;
+    spec.devices.push_back(default_device());
+    return spec;
+}
 
 // One GPU batch; the GIL is released for the duration of the call.
-void decode_rows(cb200_decoder *dec, const uint8_t *rows, uint64_t num_shots, uint64_t stride, uint8_t *obs_out, float *weight_out) {
+void decode_rows(const Handle &h, const uint8_t *rows, uint64_t num_shots, uint64_t stride, uint8_t *obs_out, float *weight_out) {
     int rc;
     {
         py::gil_scoped_release release;
-        rc = cb200_decode_batch(dec, rows, num_shots, stride, obs_out, weight_out, nullptr, CB200_IO_HOST, nullptr);
+        rc = h.multi ? cb200_multi_decode_batch(h.multi, rows, num_shots, stride, obs_out, weight_out, nullptr, nullptr)
+                     : cb200_decode_batch(h.dec, rows, num_shots, stride, obs_out, weight_out, nullptr, CB200_IO_HOST, nullptr);
     }
     if (rc != CB200_OK) raise_last(rc);
 }
@@ -78,8 +115,8 @@ struct CompiledDecoder {
     uint64_t num_detector_bytes;
     uint64_t num_observable_bytes;
 
-    static CompiledDecoder from_text(const std::string &dem_text, int device) {
-        auto h = std::make_shared<Handle>(dem_text, device);
+    static CompiledDecoder from_text(const std::string &dem_text, const DeviceSpec &spec) {
+        auto h = std::make_shared<Handle>(dem_text, spec);
         return CompiledDecoder{h, cb200_num_detectors(h->dec), cb200_num_detector_bytes(h->dec), cb200_num_observable_bytes(h->dec)};
     }
 
@@ -88,7 +125,7 @@ struct CompiledDecoder {
         if (!type_name.contains("stim.") || !type_name.contains(".DetectorErrorModel")) {
             throw std::invalid_argument("dem must be a stim.DetectorErrorModel.");
         }
-        return from_text(py::cast<std::string>(py::str(dem)), device_from(device));
+        return from_text(py::cast<std::string>(py::str(dem)), device_spec_from(device));
     }
 
     py::object predict(const py::object &dets_obj, bool include_weight) {
@@ -134,7 +171,7 @@ struct CompiledDecoder {
             dets = py::array_t<uint8_t, py::array::c_style | py::array::forcecast>(dets);
             shot_stride = (py::ssize_t)num_detector_bytes;
         }
-        decode_rows(h->dec, dets.data(), num_shots, (uint64_t)shot_stride, result_buf.mutable_data(),
+        decode_rows(*h, dets.data(), num_shots, (uint64_t)shot_stride, result_buf.mutable_data(),
                     include_weight ? weight_buf.mutable_data() : nullptr);
         if (include_weight) return py::make_tuple(result_buf, weight_buf);
         return std::move(result_buf);
@@ -161,7 +198,7 @@ struct SinterCompiledDecoder {
         }
         size_t num_shots = rows.shape(0);
         py::array_t<uint8_t> out({(py::ssize_t)num_shots, (py::ssize_t)num_observable_bytes});
-        decode_rows(h->dec, rows.data(), num_shots, (uint64_t)stride, out.mutable_data(), nullptr);
+        decode_rows(*h, rows.data(), num_shots, (uint64_t)stride, out.mutable_data(), nullptr);
         return out;
     }
 };
@@ -186,14 +223,14 @@ struct SinterDecoder {
 
     SinterCompiledDecoder compile_decoder_for_dem(const py::object &dem) {
         // no type check on this path (sinter_compat.pybind.cc:134-136)
-        auto h = std::make_shared<Handle>(py::cast<std::string>(py::str(dem)), default_device());
+        auto h = std::make_shared<Handle>(py::cast<std::string>(py::str(dem)), default_spec());
         return SinterCompiledDecoder{h, cb200_num_detector_bytes(h->dec), cb200_num_observable_bytes(h->dec)};
     }
 
     // b8 records in, b8 records out (sinter_compat.pybind.cc:96-132); the whole file is one GPU batch.
     void decode_via_files(uint64_t num_shots, uint64_t num_dets, uint64_t num_obs, const py::object &dem_path,
                           const py::object &dets_b8_in_path, const py::object &obs_predictions_b8_out_path, const py::object &) {
-        Handle h(read_text_file(py::cast<std::string>(py::str(dem_path))), default_device());
+        Handle h(read_text_file(py::cast<std::string>(py::str(dem_path))), default_spec());
         const uint64_t nb = (num_dets + 7) / 8, ob = (num_obs + 7) / 8, dob = cb200_num_observable_bytes(h.dec);
         if (nb != cb200_num_detector_bytes(h.dec)) throw std::invalid_argument("num_dets does not match the detector error model");
         std::vector<uint8_t> dets(num_shots * nb), pred(num_shots * dob), out(num_shots * ob, 0);
@@ -203,7 +240,7 @@ struct SinterDecoder {
         size_t got = fread(dets.data(), 1, dets.size(), fin);
         fclose(fin);
         if (got != dets.size()) throw std::invalid_argument("dets_b8_in_path holds fewer than num_shots records");
-        if (num_shots) decode_rows(h.dec, dets.data(), num_shots, nb, pred.data(), nullptr);
+        if (num_shots) decode_rows(h, dets.data(), num_shots, nb, pred.data(), nullptr);
         const uint8_t last_mask = (num_obs % 8) ? (uint8_t)((1u << (num_obs % 8)) - 1) : 0xFF;
         for (uint64_t s = 0; s < num_shots; s++) {
             for (uint64_t k = 0; k < ob && k < dob; k++) out[s * ob + k] = pred[s * dob + k];

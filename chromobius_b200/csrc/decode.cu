@@ -6,8 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -257,7 +259,8 @@ struct DeviceBuf {
 }  // namespace
 
 struct cb200_decoder {
-    HostTables host;
+    std::shared_ptr<const HostTables> host_ptr;  // shared by the per-device replicas of one cb200_multi
+    const HostTables &host_ref() const { return *host_ptr; }
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -293,7 +296,7 @@ namespace {
 // All read-only tables live in ONE allocation so that a single L2 access-policy window can pin them: the matcher
 // graph is re-read by every ball of every shot, while the per-shot scratch streams through L2 behind it.
 void upload_tables(cb200_decoder *d) {
-    const HostTables &h = d->host;
+    const HostTables &h = d->host_ref();
     size_t total = 0;
     auto reserve = [&](size_t bytes) {
         size_t off = total;
@@ -450,7 +453,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     // With a near table the Dijkstra search is a rare fallback and runs in the global tables; shared memory then only
     // holds the shot's row and the blossom scratch pool, which leaves most of the SM's unified storage to the L1 cache
     // (the per-event arrays of the shots in flight live there). Without a near table every ball is a search: shared tables.
-    const bool near = d->host.near_stride != 0;
+    const bool near = d->host_ref().near_stride != 0;
     uint32_t sh = d->tune_ht_log2 ? d->tune_ht_log2 : (near ? 0 : 8);
     uint32_t gl = std::min<uint32_t>(full, 14 + 3 * escalation);
     pl.cfg.sh_ht_log2 = std::min(sh, gl);
@@ -683,7 +686,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         }
         d_wi = nullptr;
     }
-    k_finish<<<(n + 255) / 256, 256, 0, s>>>(d->d_obs64.ptr, d->d_wint.ptr, n, ob, 1.0 / d->host.normalising_constant,
+    k_finish<<<(n + 255) / 256, 256, 0, s>>>(d->d_obs64.ptr, d->d_wint.ptr, n, ob, 1.0 / d->host_ref().normalising_constant,
                                             d_obs_bytes, d_wf, d_wi);
     CUDA_CHECK(cudaGetLastError());
     launches++;
@@ -747,37 +750,38 @@ extern "C" {
 
 const char *cb200_last_error(void) { return g_error.c_str(); }
 
+// Uploads already compiled tables to `device` and returns a decoder bound to it.
+static cb200_decoder *create_decoder(std::shared_ptr<const HostTables> tables, int device) {
+    std::unique_ptr<cb200_decoder, void (*)(cb200_decoder *)> d(new cb200_decoder(), cb200_free);
+    d->host_ptr = std::move(tables);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw CudaError(std::string("chromobius_b200 needs a CUDA device and has no CPU fallback: ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "no devices found"));
+    if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
+    d->device = device;
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (auto &e2 : d->ev) CUDA_CHECK(cudaEventCreate(&e2));
+    upload_tables(d.get());
+    return d.release();
+}
+
 int cb200_compile(const char *dem_text, int device, cb200_decoder **out) {
     if (!out) {
         g_error = "out must not be null";
         return CB200_ERR_INVALID_ARGUMENT;
     }
     *out = nullptr;
-    cb200_decoder *d = nullptr;
-    int rc = guarded([&]() {
+    return guarded([&]() {
         if (!dem_text) throw std::invalid_argument("dem_text must not be null");
-        d = new cb200_decoder();
-        d->host = compile_tables_cached(dem_text);
-        int count = 0;
-        cudaError_t e = cudaGetDeviceCount(&count);
-        if (e != cudaSuccess || count == 0)
-            throw CudaError(std::string("chromobius_b200 needs a CUDA device and has no CPU fallback: ") +
-                            (e != cudaSuccess ? cudaGetErrorString(e) : "no devices found"));
-        if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
-        d->device = device;
-        CUDA_CHECK(cudaSetDevice(device));
-        CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-        for (auto &e2 : d->ev) CUDA_CHECK(cudaEventCreate(&e2));
-        upload_tables(d);
+        // host compile first: a malformed model is reported as such even where no GPU exists
+        auto tables = std::make_shared<const HostTables>(compile_tables_cached(dem_text));
+        *out = create_decoder(std::move(tables), device);
         return CB200_OK;
     });
-    if (rc != CB200_OK) {
-        cb200_free(d);
-        return rc;
-    }
-    *out = d;
-    return CB200_OK;
 }
 
 void cb200_free(cb200_decoder *d) {
@@ -796,16 +800,16 @@ void cb200_free(cb200_decoder *d) {
     delete d;
 }
 
-uint64_t cb200_num_detectors(const cb200_decoder *d) { return d->host.num_dets; }
-uint64_t cb200_num_observables(const cb200_decoder *d) { return d->host.num_obs; }
-uint64_t cb200_num_detector_bytes(const cb200_decoder *d) { return (d->host.num_dets + 7) / 8; }
-uint64_t cb200_num_observable_bytes(const cb200_decoder *d) { return (d->host.num_obs + 7) / 8; }
-double cb200_normalising_constant(const cb200_decoder *d) { return d->host.normalising_constant; }
+uint64_t cb200_num_detectors(const cb200_decoder *d) { return d->host_ref().num_dets; }
+uint64_t cb200_num_observables(const cb200_decoder *d) { return d->host_ref().num_obs; }
+uint64_t cb200_num_detector_bytes(const cb200_decoder *d) { return (d->host_ref().num_dets + 7) / 8; }
+uint64_t cb200_num_observable_bytes(const cb200_decoder *d) { return (d->host_ref().num_obs + 7) / 8; }
+double cb200_normalising_constant(const cb200_decoder *d) { return d->host_ref().normalising_constant; }
 uint64_t cb200_table_bytes(const cb200_decoder *d) { return d->table_bytes; }
-uint64_t cb200_graph_half_edges(const cb200_decoder *d) { return d->host.adj.size(); }
+uint64_t cb200_graph_half_edges(const cb200_decoder *d) { return d->host_ref().adj.size(); }
 
 char *cb200_describe(const cb200_decoder *d) {
-    std::string s = d->host.describe();
+    std::string s = d->host_ref().describe();
     char *r = (char *)malloc(s.size() + 1);
     if (r) memcpy(r, s.c_str(), s.size() + 1);
     return r;
@@ -862,6 +866,112 @@ int cb200_decode_shot_edges(cb200_decoder *d, const uint8_t *dets_row, int64_t *
         if (num_edge_ints) *num_edge_ints = need;
         return rc;
     });
+}
+
+// ---- one decoder replicated over several GPUs of the box (include/chromobius_b200.h) ----------------------------------
+struct cb200_multi {
+    std::vector<cb200_decoder *> replicas;
+};
+
+int cb200_compile_multi(const char *dem_text, const int *devices, int num_devices, cb200_multi **out) {
+    if (!out) {
+        g_error = "out must not be null";
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    return guarded([&]() {
+        if (!dem_text) throw std::invalid_argument("dem_text must not be null");
+        auto tables = std::make_shared<const HostTables>(compile_tables_cached(dem_text));
+        std::vector<int> devs;
+        if (devices && num_devices > 0) {
+            devs.assign(devices, devices + num_devices);
+        } else {
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+                throw CudaError("chromobius_b200 needs a CUDA device and has no CPU fallback: no devices found");
+            for (int k = 0; k < count; k++) devs.push_back(k);
+        }
+        std::unique_ptr<cb200_multi> m(new cb200_multi());
+        try {
+            for (int dev : devs) m->replicas.push_back(create_decoder(tables, dev));
+        } catch (...) {
+            for (auto *r : m->replicas) cb200_free(r);
+            throw;
+        }
+        *out = m.release();
+        return CB200_OK;
+    });
+}
+
+void cb200_multi_free(cb200_multi *m) {
+    if (!m) return;
+    for (auto *r : m->replicas) cb200_free(r);
+    delete m;
+}
+
+int cb200_multi_num_devices(const cb200_multi *m) { return m ? (int)m->replicas.size() : 0; }
+
+cb200_decoder *cb200_multi_replica(cb200_multi *m, int index) {
+    return (m && index >= 0 && index < (int)m->replicas.size()) ? m->replicas[index] : nullptr;
+}
+
+int cb200_multi_decode_batch(cb200_multi *m, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
+                             float *weight_out, int64_t *weight_int_out, cb200_batch_stats *stats) {
+    if (!m || m->replicas.empty()) {
+        g_error = "multi-GPU decoder must not be null";
+        return CB200_ERR_INVALID_ARGUMENT;
+    }
+    const uint64_t G = m->replicas.size();
+    const uint64_t ob = cb200_num_observable_bytes(m->replicas[0]);
+    // contiguous row ranges, one host thread and one stream per device; results land in the caller's buffers
+    std::vector<int> rc(G, CB200_OK);
+    std::vector<std::string> err(G);
+    std::vector<cb200_batch_stats> st(G);
+    std::vector<uint64_t> first(G + 1, 0);
+    for (uint64_t k = 0; k <= G; k++) first[k] = num_shots * k / G;
+    std::vector<std::thread> threads;
+    for (uint64_t k = 0; k < G; k++) {
+        threads.emplace_back([&, k]() {
+            const uint64_t a = first[k], n = first[k + 1] - first[k];
+            st[k] = cb200_batch_stats{};
+            st[k].first_failed_shot = -1;
+            if (n == 0) return;
+            rc[k] = cb200_decode_batch(m->replicas[k], dets ? dets + a * row_stride : nullptr, n, row_stride,
+                                       obs_out ? obs_out + a * ob : nullptr, weight_out ? weight_out + a : nullptr,
+                                       weight_int_out ? weight_int_out + a : nullptr, CB200_IO_HOST, &st[k]);
+            if (rc[k] != CB200_OK) err[k] = cb200_last_error();  // thread-local in the worker: carried back by hand
+        });
+    }
+    for (auto &t : threads) t.join();
+    cb200_batch_stats total{};
+    total.first_failed_shot = -1;
+    int result = CB200_OK;
+    for (uint64_t k = 0; k < G; k++) {
+        total.num_shots += st[k].num_shots;
+        total.num_detection_events += st[k].num_detection_events;
+        total.num_retried_shots += st[k].num_retried_shots;
+        total.num_failed_shots += st[k].num_failed_shots;
+        if (total.first_failed_shot < 0 && st[k].first_failed_shot >= 0) {
+            total.first_failed_shot = st[k].first_failed_shot + (int64_t)first[k];
+            total.first_failed_status = st[k].first_failed_status;
+        }
+        total.max_events_per_shot = std::max(total.max_events_per_shot, st[k].max_events_per_shot);
+        total.group_threads = st[k].group_threads ? st[k].group_threads : total.group_threads;
+        total.num_groups += st[k].num_groups;
+        total.kernel_launches += st[k].kernel_launches;
+        total.ms_h2d = std::max(total.ms_h2d, st[k].ms_h2d);
+        total.ms_count = std::max(total.ms_count, st[k].ms_count);
+        total.ms_decode = std::max(total.ms_decode, st[k].ms_decode);
+        total.ms_d2h = std::max(total.ms_d2h, st[k].ms_d2h);
+        total.ms_total = std::max(total.ms_total, st[k].ms_total);
+        total.matcher_rounds += st[k].matcher_rounds;
+        if (rc[k] != CB200_OK && result == CB200_OK) {
+            result = rc[k];
+            g_error = err[k];
+        }
+    }
+    if (stats) *stats = total;
+    return result;
 }
 
 }  // extern "C"

@@ -36,6 +36,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t &state) {
     return z ^ (z >> 31);
 }
 
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 constexpr int SAMPLER_WARPS = 4;
 
 __global__ void __launch_bounds__(SAMPLER_WARPS * 32) k_sample_dem(
@@ -56,8 +63,10 @@ __global__ void __launch_bounds__(SAMPLER_WARPS * 32) k_sample_dem(
             uint64_t len = pc.end - pc.start;
             uint32_t lo = pc.start + (uint32_t)(len * lane / 32), hi = pc.start + (uint32_t)(len * (lane + 1) / 32);
             if (lo >= hi) continue;
-            uint64_t st = seed * 0xD1342543DE82EF95ull + (first_shot + shot) * 0x9E3779B97F4A7C15ull + ((uint64_t)c << 40) + ((uint64_t)lane << 32);
-            splitmix64(st);
+            // One stream per (seed, shot, class, lane): the start state goes through full mixers, so that no two streams
+            // are shifted copies of each other (a start state that merely ADDS shot * the splitmix increment makes draw j
+            // of shot s + 1 equal draw j + 1 of shot s).
+            uint64_t st = mix64(mix64(seed ^ mix64(first_shot + shot)) + (((uint64_t)c << 32) | lane));
             int64_t pos = (int64_t)lo - 1;
             while (true) {
                 double u = ((double)(splitmix64(st) >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]

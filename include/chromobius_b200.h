@@ -114,6 +114,23 @@ int cb200_profile_phases(cb200_decoder *dec, int enable, unsigned long long *cyc
 uint64_t cb200_table_bytes(const cb200_decoder *dec);
 uint64_t cb200_graph_half_edges(const cb200_decoder *dec);
 
+/* ---- One decoder replicated over several GPUs of one box ---------------------------------------------------------
+ * BASELINE's largest configuration shards 10 M shots over 8 B200; shots are independent, so a batch is split into
+ * contiguous row ranges, one per device, each decoded by that device's replica on its own host thread and stream.
+ * There is no data-path collective: every range's predictions land directly in the caller's host buffers. This keeps
+ * the reference's single call (CompiledDecoder::predict_obs_flips_from_dets_bit_packed, pybind/chromobius.pybind.cc:49-117)
+ * a single call on N GPUs. The model is compiled once on the host; every device receives a copy of the tables.
+ *   devices / num_devices   GPU indices to use (NULL / 0: every visible GPU)
+ * cb200_multi_decode_batch takes HOST pointers only; `stats` (nullable) sums the per-device counters, with the times
+ * being the maximum over devices. cb200_multi_replica() exposes the per-device decoders (queries, tuning). */
+typedef struct cb200_multi cb200_multi;
+int cb200_compile_multi(const char *dem_text, const int *devices, int num_devices, cb200_multi **out);
+void cb200_multi_free(cb200_multi *m);
+int cb200_multi_num_devices(const cb200_multi *m);
+cb200_decoder *cb200_multi_replica(cb200_multi *m, int index);
+int cb200_multi_decode_batch(cb200_multi *m, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
+                             float *weight_out, int64_t *weight_int_out, cb200_batch_stats *stats);
+
 /* ---- On-device syndrome sampler: the step in front of the decode path --------------
  * Plays the role of stim::DemSampler in the reference's tests (decode/decoder_integration.test.cc:55-68): each error
  * mechanism of the DEM fires independently with its probability, a shot is the XOR of the fired symptoms.

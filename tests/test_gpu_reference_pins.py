@@ -102,7 +102,7 @@ def test_d25_weights_against_the_independent_dense_matcher(libs):
     st = dec.decode_device(d_dets.data_ptr(), S, nb, d_pred.data_ptr(), weight_int_ptr=d_w.data_ptr())
     torch.cuda.synchronize()
     assert st.num_failed_shots == 0
-    # 1900 plain shots + the 60 heaviest by weight + the 60 with most detection events of the batch
+    # 2000 plain shots + the 60 heaviest by weight + the 60 with most detection events of the batch
     heavy_w = torch.topk(d_w, 60).indices
     events = torch.zeros(S, dtype=torch.int64, device=dev)
     for lo in range(0, S, 50000):
@@ -112,7 +112,7 @@ def test_d25_weights_against_the_independent_dense_matcher(libs):
             cnt += ((blk >> b) & 1).sum(dim=1)
         events[lo:lo + 50000] = cnt
     heavy_e = torch.topk(events, 60).indices
-    pick = torch.unique(torch.cat([torch.arange(1900, device=dev), heavy_w, heavy_e]))
+    pick = torch.unique(torch.cat([torch.arange(2000, device=dev), heavy_w, heavy_e]))
     rows = d_dets[pick].cpu().numpy()
     w = d_w[pick].cpu().numpy()
     m = masks(d_pred[pick].cpu().numpy())

@@ -52,3 +52,34 @@ def test_sampled_shots_decode_consistently():
     mistakes = int((pred[:, 0].astype(np.uint64) != obs).sum())
     # published logical error rate 6.0e-3 per shot (assets/stats.csv:64); 8192-shot test count 45 (decoder_integration.test.cc:148)
     assert 60 <= mistakes <= 190, mistakes
+
+
+def test_shots_are_independent_of_each_other():
+    """Streams of different shots must not be shifted copies (round-1 bug: draw j of shot s + 1 was draw j + 1 of shot s,
+    so the first gap of one shot equalled the second gap of the previous one). One probability class, 32 x 200 errors
+    `error(p) Dk`: lane 0 of the sampling warp covers detectors 0..199."""
+    import chromobius_b200 as cb
+    n, per_lane, p = 32 * 200, 200, 0.05
+    text = '\n'.join('error(%g) D%d' % (p, k) for k in range(n)) + '\n' + \
+           '\n'.join('detector(0, 0, 0, %d) D%d' % (k % 3, k) for k in range(n)) + '\n'
+    smp = cb.DeviceDemSampler(text, device=0)
+    shots = 20000
+    dets, _ = smp.sample(shots, seed=1)
+    bits = np.unpackbits(dets, axis=1, bitorder='little')[:, :per_lane]
+    first = np.full(shots, -1)
+    second_gap = np.full(shots, -1)
+    for s in range(shots):
+        hits = np.nonzero(bits[s])[0]
+        if len(hits) >= 1:
+            first[s] = hits[0]
+        if len(hits) >= 2:
+            second_gap[s] = hits[1] - hits[0] - 1
+    ok = (first[1:] >= 0) & (second_gap[:-1] >= 0)
+    a, b = first[1:][ok].astype(float), second_gap[:-1][ok].astype(float)
+    assert len(a) > 10000
+    corr = np.corrcoef(a, b)[0, 1]
+    assert abs(corr) < 0.05, 'first gap of shot s+1 is correlated with the second gap of shot s: %.3f' % corr
+    # and rows of neighbouring shots agree no more often than rows of distant shots
+    near = (bits[1:] & bits[:-1]).sum() / (shots - 1)
+    far = (bits[100:] & bits[:-100]).sum() / (shots - 100)
+    assert abs(near - far) < 0.05

@@ -11,9 +11,12 @@ import torch.multiprocessing as mp
 
 from dem_util import read_dem, NumpyDemSampler
 
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+
 
 def test_shard_bounds_cover_everything():
-    from chromobius_b200.sharding import shard_bounds
+    from dist_sharding import shard_bounds
     for n in [0, 1, 7, 64, 1000003]:
         for w in [1, 2, 3, 8]:
             pieces = [shard_bounds(n, r, w) for r in range(w)]
@@ -28,8 +31,9 @@ def _worker(rank, world, port, name, shots, out_dir):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
     sys.path.insert(0, os.path.join(root, 'tests'))
+    sys.path.insert(0, os.path.join(root, 'tools'))
     import oracle
-    from chromobius_b200.sharding import decode_sharded
+    from dist_sharding import decode_sharded
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
