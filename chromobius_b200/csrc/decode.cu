@@ -188,7 +188,20 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
         g.sync();
         if (k >= total) break;
         uint32_t shot = p.shot_list ? p.shot_list[k] : k;
+        if (p.ready) {
+            // streaming input: wait until the copy stream has delivered this shot's row
+            if (g.tid == 0) {
+                while (*(const volatile uint32_t *)p.ready <= shot) __nanosleep(500);
+                __threadfence();
+            }
+            g.sync();
+        }
         decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
+        if (p.event_total && g.tid == 0) {
+            const uint32_t ev = s.word_rank[s.nwords];  // detection events of the shot (set by ingest_shot, also on overflow)
+            atomicAdd(p.event_total, (unsigned long long)ev);
+            atomicMax(p.event_max, ev);
+        }
         // Out of scratch: again, in a spare arena with the next level's scratch, if one is free (decode_shot ended with a
         // barrier after thread 0 stored the status). Otherwise the host's retry launch takes the shot.
         if (p.spare_arena && p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) {
@@ -206,6 +219,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
                 bind_shot(s, p, p.spare_cfg, p.spare_arena + (uint64_t)slot * p.spare_stride, shared, g);
                 decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
                 if (g.tid == 0) {
+                    // still too small: tell the host that level 1 has been tried, so its retry starts at level 2
+                    if (p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) p.status_out[shot] = SHOT_SCRATCH_OVERFLOW_SPARE;
                     __threadfence();
                     atomicExch(&p.spare_claim[slot], 0u);
                     atomicAdd(p.spare_retries, 1u);
@@ -264,6 +279,8 @@ struct cb200_decoder {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // streaming input: chunks of a large host batch (decode_impl)
+    std::vector<uint32_t> ready_values;      // host source of the "shots resident" words the copy stream publishes
     cudaEvent_t ev[6] = {};
     // device tables (one allocation, see upload_tables)
     DeviceBuf<uint8_t> d_tables;
@@ -288,7 +305,7 @@ struct cb200_decoder {
     DeviceBuf<float> d_wfloat;
     // arena layout currently initialised on the device
     // tuning
-    uint32_t tune_group = 0, tune_ht_log2 = 0, tune_pool_bytes = 24u << 10;
+    uint32_t tune_group = 0, tune_ht_log2 = 0, tune_pool_bytes = 32u << 10;
 };
 
 namespace {
@@ -461,6 +478,7 @@ Plan make_plan(cb200_decoder *d, uint64_t work_items, uint32_t max_det_events, d
     if (const char *env = getenv("CB200_SH_EVENTS")) pl.cfg.sh_events = (uint32_t)strtoul(env, nullptr, 10);  // experiments
     if (const char *env = getenv("CB200_POOL_KB")) pl.cfg.sh_pool = near ? (uint32_t)strtoul(env, nullptr, 10) << 10 : 0;  // experiments
     pl.cfg.sh_found = 16;
+    if (getenv("CB200_NO_PLAIN_LIFT")) pl.cfg.pad |= 1u;  // experiments / tests: always the general lift
     pl.cfg.ht_log2 = gl;
     pl.cfg.found_cap = 256u << (2 * escalation);
     // Event capacity in coarse steps, and sticky: a batch that fits the layout the arena already has keeps it, so a
@@ -547,38 +565,52 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     CUDA_CHECK(cudaEventRecord(d->ev[0], s));
     const uint8_t *d_dets = dets;
     uint64_t d_stride = row_stride;
-    if (!dev_io) {
-        if (nb) {
-            d->d_dets.ensure((size_t)n * nb);
-            CUDA_CHECK(cudaMemcpy2DAsync(d->d_dets.ptr, nb, dets, row_stride, nb, n, cudaMemcpyHostToDevice, s));
-        }
-        d_dets = d->d_dets.ptr;
-        d_stride = nb;
-    }
-    CUDA_CHECK(cudaEventRecord(d->ev[1], s));
-
     d->d_obs64.ensure(n);
     d->d_wint.ensure(n);
     d->d_status.ensure(n);
     d->d_rounds.ensure(n);
     d->d_counts.ensure(n);
-    d->d_scalars.ensure(8);
-    CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr, 0, 8 * sizeof(uint32_t), s));
-    // scalars: [0] max count, [2..3] total (u64), [4] work counter
+    d->d_scalars.ensure(16);
+    CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr, 0, 16 * sizeof(uint32_t), s));
+    // scalars: [0] max count, [2..3] total (u64) of k_count_events, [4] work counter, [5] spare retries,
+    //          [6] ready shots (streaming input), [8..9] total (u64) and [10] max gathered by the decode kernel
+    // Streaming input: a large host batch is copied in chunks on a second stream while the persistent decode kernel
+    // already works on the chunks that have arrived. The arena is sized from the first chunk (plus head room; a shot
+    // beyond it takes the scratch-overflow retry path), so the kernel can start after one chunk instead of after the
+    // whole copy and a count pass over all of it.
+    uint64_t chunk = 0;
+    if (!dev_io && nb && !getenv("CB200_NO_PIPELINE")) {
+        chunk = std::max<uint64_t>(8192, ((uint64_t)96 << 20) / nb);
+        if (const char *env = getenv("CB200_PIPELINE_CHUNK")) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+        if ((uint64_t)n < 3 * chunk) chunk = 0;
+    }
+    const bool streaming = chunk != 0;
+    const uint32_t counted = streaming ? (uint32_t)chunk : n;  // shots that k_count_events looks at
+    if (!dev_io) {
+        if (nb) {
+            d->d_dets.ensure((size_t)n * nb);
+            CUDA_CHECK(cudaMemcpy2DAsync(d->d_dets.ptr, nb, dets, row_stride, nb, counted, cudaMemcpyHostToDevice, s));
+        }
+        d_dets = d->d_dets.ptr;
+        d_stride = nb;
+    }
+    CUDA_CHECK(cudaEventRecord(d->ev[1], s));
     {
-        uint32_t blocks = std::min<uint32_t>((n + 7) / 8, (uint32_t)d->num_sms * 8);
-        k_count_events<<<blocks, 256, 0, s>>>(d_dets, d_stride, n, d->dview.ingest_mask, nb, d->d_counts.ptr, d->d_scalars.ptr,
+        uint32_t blocks = std::min<uint32_t>((counted + 7) / 8, (uint32_t)d->num_sms * 8);
+        k_count_events<<<blocks, 256, 0, s>>>(d_dets, d_stride, counted, d->dview.ingest_mask, nb, d->d_counts.ptr, d->d_scalars.ptr,
                                               (unsigned long long *)(d->d_scalars.ptr + 2));
         CUDA_CHECK(cudaGetLastError());
         launches++;
     }
-    uint32_t scal[8];
+    uint32_t scal[16];
     CUDA_CHECK(cudaMemcpyAsync(scal, d->d_scalars.ptr, sizeof(scal), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaEventRecord(d->ev[2], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     uint32_t max_count = scal[0];
     uint64_t total_events;
     memcpy(&total_events, &scal[2], 8);
+    const double mean_events = (double)total_events / (double)counted;
+    if (streaming) max_count += std::max<uint32_t>(32, max_count / 8);  // head room for the chunks not seen yet
     st.num_detection_events = total_events;
     st.max_events_per_shot = 2 * max_count;
 
@@ -592,6 +624,8 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     p.status_out = d->d_status.ptr;
     p.rounds_out = d->d_rounds.ptr;
     p.work_counter = d->d_scalars.ptr + 4;
+    p.event_total = (unsigned long long *)(d->d_scalars.ptr + 8);
+    p.event_max = d->d_scalars.ptr + 10;
     if (d->profile_phases) {
         d->d_phase.ensure(24);
         CUDA_CHECK(cudaMemsetAsync(d->d_phase.ptr, 0, 192, s));
@@ -605,10 +639,14 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     }
 
     std::vector<uint32_t> status(n);
-    std::vector<uint32_t> retry;
+    std::vector<uint32_t> retry, deferred;  // deferred: already failed in a level-1 spare arena, joins the list at level 2
     for (uint32_t esc = 0; esc < 4; esc++) {
+        if (esc == 1 && retry.empty()) {
+            retry.swap(deferred);
+            continue;
+        }
         uint64_t items = esc == 0 ? n : retry.size();
-        Plan pl = make_plan(d, items, max_count, (double)total_events / (double)n, esc);
+        Plan pl = make_plan(d, items, max_count, mean_events, esc);
         ensure_arena(d, pl, p, launches, esc);
         p.spare_arena = nullptr;
         p.num_spares = 0;
@@ -622,7 +660,7 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
             constexpr uint32_t NUM_SPARES = 16;
             const bool no_spares = getenv("CB200_NO_SPARES") != nullptr;  // experiments / tests
             if (!no_spares && n > pl.groups) {
-                Plan sp = make_plan(d, NUM_SPARES, max_count, (double)total_events / (double)n, 1);
+                Plan sp = make_plan(d, NUM_SPARES, streaming ? 2 * max_count : max_count, mean_events, 1);
                 if (sp.group == pl.group && sp.smem_per_group == pl.smem_per_group && sp.cfg.sh_ht_log2 == pl.cfg.sh_ht_log2 &&
                     sp.cfg.sh_pool == pl.cfg.sh_pool && sp.cfg.sh_events == pl.cfg.sh_events && sp.cfg.sh_found == pl.cfg.sh_found &&
                     sp.cfg.max_events >= pl.cfg.max_events) {
@@ -645,6 +683,18 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
             p.list_len = (uint32_t)retry.size();
             CUDA_CHECK(cudaMemsetAsync(d->d_scalars.ptr + 4, 0, 4, s));
         }
+        p.ready = nullptr;
+        if (esc == 0 && streaming) {
+            // the first chunk is resident; the kernel starts now and the copy stream feeds it
+            d->ready_values.assign(((uint64_t)n + chunk - 1) / chunk + 1, 0);
+            d->ready_values[0] = counted;
+            CUDA_CHECK(cudaMemcpyAsync(d->d_scalars.ptr + 6, &d->ready_values[0], 4, cudaMemcpyHostToDevice, s));
+            p.ready = d->d_scalars.ptr + 6;
+        }
+        if (esc != 0) {
+            p.event_total = nullptr;
+            p.event_max = nullptr;
+        }
         if (pl.group == 32) launch_decode<32>(p, pl.groups, pl.smem_per_group, s);
         else if (pl.group == 128) launch_decode<128>(p, pl.groups, pl.smem_per_group, s);
         else if (pl.group == 192) launch_decode<192>(p, pl.groups, pl.smem_per_group, s);
@@ -653,17 +703,48 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
         CUDA_CHECK(cudaGetLastError());
         launches++;
         if (esc == 0) CUDA_CHECK(cudaEventRecord(d->ev[3], s));
+        if (esc == 0 && streaming) {
+            // remaining chunks on the copy stream; after each, the number of resident shots is published
+            if (!d->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+            uint64_t k = 1;
+            for (uint64_t first = counted; first < n; first += chunk, k++) {
+                const uint64_t rows = std::min<uint64_t>(chunk, n - first);
+                CUDA_CHECK(cudaMemcpy2DAsync(d->d_dets.ptr + first * nb, nb, dets + first * row_stride, row_stride, nb, rows,
+                                             cudaMemcpyHostToDevice, d->copy_stream));
+                d->ready_values[k] = (uint32_t)(first + rows);
+                CUDA_CHECK(cudaMemcpyAsync(d->d_scalars.ptr + 6, &d->ready_values[k], 4, cudaMemcpyHostToDevice, d->copy_stream));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
+        }
         CUDA_CHECK(cudaMemcpyAsync(status.data(), d->d_status.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         uint32_t spare_retries = 0;
         if (p.spare_arena) CUDA_CHECK(cudaMemcpyAsync(&spare_retries, d->d_scalars.ptr + 5, 4, cudaMemcpyDeviceToHost, s));
+        uint32_t gathered[4] = {0, 0, 0, 0};
+        if (esc == 0) CUDA_CHECK(cudaMemcpyAsync(gathered, d->d_scalars.ptr + 8, sizeof(gathered), cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+        if (esc == 0 && streaming) {
+            // what the first chunk could only estimate: exact totals from the kernel, used by the statistics and by the
+            // retry levels' plans
+            memcpy(&total_events, &gathered[0], 8);
+            max_count = std::max(max_count, gathered[2]);
+            st.num_detection_events = total_events;
+            st.max_events_per_shot = 2 * gathered[2];
+        }
         st.num_retried_shots += spare_retries;
         retry.clear();
-        for (uint32_t k = 0; k < n; k++)
+        for (uint32_t k = 0; k < n; k++) {
             if (status[k] == SHOT_SCRATCH_OVERFLOW) retry.push_back(k);
-        if (retry.empty()) break;
-        st.num_retried_shots += retry.size();
+            else if (status[k] == SHOT_SCRATCH_OVERFLOW_SPARE) deferred.push_back(k);
+        }
+        if (esc >= 1) {
+            retry.insert(retry.end(), deferred.begin(), deferred.end());
+            deferred.clear();
+        }
+        if (retry.empty() && deferred.empty()) break;
+        st.num_retried_shots += retry.size() + (esc == 0 ? deferred.size() : 0);
     }
+    for (uint32_t k = 0; k < n; k++)
+        if (status[k] == SHOT_SCRATCH_OVERFLOW_SPARE) status[k] = SHOT_SCRATCH_OVERFLOW;  // one public code for "out of scratch"
     for (uint32_t k = 0; k < n; k++)
         if (status[k]) {
             if (st.first_failed_shot < 0) {
@@ -796,6 +877,7 @@ void cb200_free(cb200_decoder *d) {
     d->d_scalars.release(); d->d_list.release(); d->d_spare_claim.release(); d->d_wfloat.release(); d->d_phase.release();
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }

@@ -61,6 +61,7 @@ enum ShotStatus : uint32_t {
     SHOT_DISCHARGE_FAILED = 4,      // "Failed to lift a flattened edge cycle ..."   (decoder.cc:176-202)
     SHOT_ROUND_LIMIT = 5,
     SHOT_COMPONENT_TOO_LARGE = 6,   // a matching component exceeded MAX_COMPONENT events
+    SHOT_SCRATCH_OVERFLOW_SPARE = 7,  // out of scratch again in a spare (level-1) arena: the host retries from level 2
 };
 
 constexpr uint32_t MAX_COMPONENT = 2000;      // larger matching components are reported, not decoded
@@ -90,7 +91,7 @@ struct ScratchConfig {
     uint64_t dyn_bytes;   // dynamic region (neighbour lists, blossom scratch, paths, Euler arrays)
     uint32_t sh_events;   // per-event arrays kept in shared memory instead of the arena: bit 0 uf + root, bit 1 pc + the
                           // flag bytes, bit 2 h (each only when max_events entries fit the launch's shared memory)
-    uint32_t pad;
+    uint32_t pad;         // experiment / test switches: bit 0 = never take the plain-cycle lift (lift_shot_plain)
 };
 
 // Launch-wide parameters.
@@ -131,6 +132,13 @@ struct DecodeParams {
     // [19] ball pops [20] cycles inside ball_grow [21] balls [22] nodes touched by balls [23] ball queries answered by
     // the near table
     unsigned long long *phase_cycles;
+    // Streaming input (nullable): the host copies the batch in chunks while this kernel already decodes; *ready is the
+    // number of leading shots whose rows have arrived (written by the copy stream after each chunk). A group that draws
+    // a shot index at or beyond it waits.
+    const uint32_t *ready;
+    // Batch statistics gathered by the first-level launch (nullable): total and maximum detection events per shot.
+    unsigned long long *event_total;
+    uint32_t *event_max;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -202,6 +210,10 @@ struct HostGroup {
     CB_HD uint64_t min64(uint64_t v) const { return v; }
     CB_HD uint64_t xor64(uint64_t v) const { return v; }
     CB_HD uint64_t add64(uint64_t v) const { return v; }
+};
+
+struct alignas(16) U4 {
+    uint32_t x, y, z, w;
 };
 
 CB_HD uint64_t align16(uint64_t x) { return (x + 15) & ~uint64_t{15}; }
@@ -508,14 +520,58 @@ CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_
 template <class G>
 CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
     const uint32_t nb = s.T.num_det_bytes;
-    for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
-        uint32_t v = 0;
-        for (uint32_t b = 0; b < 4; b++) {
-            uint32_t k = 4 * w + b;
-            if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
+    const uint32_t full = nb / 4;  // words that lie completely inside the row
+    if ((((uintptr_t)row) & 3u) == 0 && full) {
+        // 4-byte aligned row (every row of a contiguous batch whose detector byte count is a multiple of 4, e.g. 3076 at
+        // d25 r100): words up to the first 16-byte boundary one by one, then 16-byte vector loads, four words each, then
+        // the rest. The mask table is 16-byte aligned (tables.h) and is read the same way.
+        const uint32_t *row32 = (const uint32_t *)row;
+        const uint32_t *mask32 = (const uint32_t *)s.T.ingest_mask;
+        uint32_t head = (uint32_t)(((16u - (uint32_t)((uintptr_t)row & 15u)) & 15u) >> 2);
+        if (head > full) head = full;
+        const uint32_t body = (full - head) / 4;
+        for (uint32_t w = g.tid; w < head; w += g.n) {
+            const uint32_t v = row32[w] & mask32[w];
+            s.words[w] = v;
+            s.word_rank[w] = popc32(v);
         }
-        s.words[w] = v;
-        s.word_rank[w] = popc32(v);
+        const U4 *row128 = (const U4 *)(row32 + head);
+        for (uint32_t k = g.tid; k < body; k += g.n) {
+            const U4 r = row128[k];
+            const uint32_t w = head + 4 * k;
+            const uint32_t v0 = r.x & mask32[w], v1 = r.y & mask32[w + 1], v2 = r.z & mask32[w + 2], v3 = r.w & mask32[w + 3];
+            s.words[w] = v0;
+            s.words[w + 1] = v1;
+            s.words[w + 2] = v2;
+            s.words[w + 3] = v3;
+            s.word_rank[w] = popc32(v0);
+            s.word_rank[w + 1] = popc32(v1);
+            s.word_rank[w + 2] = popc32(v2);
+            s.word_rank[w + 3] = popc32(v3);
+        }
+        for (uint32_t w = head + 4 * body + g.tid; w < s.nwords; w += g.n) {
+            uint32_t v = 0;
+            if (w < full) {
+                v = row32[w] & mask32[w];
+            } else {
+                for (uint32_t b = 0; b < 4; b++) {
+                    const uint32_t k = 4 * w + b;
+                    if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
+                }
+            }
+            s.words[w] = v;
+            s.word_rank[w] = popc32(v);
+        }
+    } else {
+        for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
+            uint32_t v = 0;
+            for (uint32_t b = 0; b < 4; b++) {
+                uint32_t k = 4 * w + b;
+                if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
+            }
+            s.words[w] = v;
+            s.word_rank[w] = popc32(v);
+        }
     }
     if (g.tid == 0) {
         s.hdr->status = 0;
@@ -812,9 +868,6 @@ CB_HD const NbEntry *nb_list(const Shot &s, uint32_t i) { return (const NbEntry 
 // (tables.h), so a ball query is a scan of the row against the shot's event bits. Both routines return false when the
 // row ends before the query is decided; the caller then runs the Dijkstra search, which gives the same answer.
 // ---------------------------------------------------------------------------------------------------------------
-struct alignas(16) U4 {
-    uint32_t x, y, z, w;
-};
 CB_HD const NearEntry *near_at(const TablesView &T, uint32_t node, uint32_t p) {
     return T.near + ((uint64_t)(p >> 5) * T.num_nodes + node) * 32 + (p & 31);
 }
@@ -1858,11 +1911,13 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     return false;
 }
 
-// Scratch bytes of the solver class that handles n events: fixed layouts of 8, 16 and 32 vertices (shared memory only), the
-// run-time sized layout beyond.
+// Scratch bytes of the solver class that handles n events: fixed layouts of 16 and 32 vertices (shared memory only), the
+// run-time sized layout beyond. A third fixed class for <= 8 vertices (-DCB_CAP8) saves pool space but costs a fourth copy
+// of the 41 KB solver body; without it every class runs 5-12 % faster (instruction cache) and, with a 32 KB pool, the
+// step gets 2.5 % shorter (measured at d25 r100, profiles/r02_kernel_experiments.txt).
 template <class G>
 CB_HD uint64_t blossom_bytes(uint32_t n) {
-#ifndef CB_NO_CAP8
+#ifdef CB_CAP8
     if (n <= 8) return Blossom<G, 8>::bytes_needed((int)n);
 #endif
     if (n <= 16) return Blossom<G, 16>::bytes_needed((int)n);
@@ -1979,7 +2034,7 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
 template <class G>
 CB_HD void solve_component_blossom(Shot &s, const G &g, uint32_t c, uint8_t *scratch) {
     const uint32_t n = s.cnt[s.comp_root[c]];
-#ifndef CB_NO_CAP8
+#ifdef CB_CAP8
     if (scratch && n <= 8) solve_component_blossom_t<G, 8>(s, g, c, scratch);
     else
 #endif
@@ -2685,6 +2740,169 @@ CB_HDN void lift_component(Shot &s, const LiftArrays &L, uint32_t root, uint32_t
     s.fail(SHOT_DISCHARGE_FAILED);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Plain-cycle lift. When no Moebius node takes part in more than one matched path -- no path runs through another
+// pair's event node and no two paths share an interior node -- every node of the shot's Euler graph has exactly two
+// half-edges (event nodes: their path and their doubling edge), every component is one plain cycle, and the
+// reference's tour (euler_tours.cc:64-97) is forced: it starts at the first node of the component's first matcher
+// edge, which is the node of the component's smallest event index (pairs are emitted in ascending order of their
+// smaller event, each path from the smaller event to the larger), leaves along that event's path, and alternates
+// paths and doubling edges until it is back. That cycle is produced here straight from the pair list and the stored
+// paths, one thread per detection event: the thread walks from its even event and gives up as soon as it meets a
+// smaller event index, so exactly the component's minimum finishes the walk, stores the cycle and discharges it.
+// None of the half-edge arrays of the general lift (below) are built: the scratch of this stage drops from ~65 to
+// ~10 bytes per half-edge. At d25 r100 nearly every matched pair is a direct edge (784 path edges for 771 pairs) and
+// shots with a junction are rare; those take the general lift, which gives identical cycles for plain components.
+// ---------------------------------------------------------------------------------------------------------------
+// Drag-table index of the step a -> b (decoder.cc:104-127 looks the detector pair up in mmm).
+CB_HD uint32_t step_drag_index(const TablesView &T, uint32_t a, uint32_t b) {
+    if ((a >> 1) == (b >> 1)) return T.self_drag[a >> 1];
+    const uint32_t he = find_half_edge(T, a, b);
+    return he != NO_INDEX ? T.adj_drag[he] : NO_INDEX;
+}
+
+// Walks the cycle that starts at event i0 (an even event index). Returns the number of cycle nodes, or 0 when a
+// smaller event index turned up (i0 is not the component's minimum) or the walk did not close. With `cyc` set, also
+// stores the nodes and the drag index of the step that arrives at each of them (cyc_di[0] belongs to the closing step).
+CB_HDN uint32_t plain_cycle_walk(Shot &s, uint32_t i0, uint32_t *cyc, uint32_t *cyc_di, uint32_t limit) {
+    uint32_t len = 1;
+    uint32_t cur_node = s.event_node(i0);
+    if (cyc) cyc[0] = cur_node;
+    uint32_t c = i0;
+    while (true) {
+        const int32_t pj = s.partner[c];
+        if (pj < 0) return 0;
+        const uint32_t j = (uint32_t)pj;
+        if (j < i0 || (j ^ 1u) < i0) return 0;
+        const uint32_t owner = c < j ? c : j;
+        const uint32_t plen = s.path_len[owner];
+        if (plen < 2) return 0;
+        const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[owner] << 4));
+        for (uint32_t k = 1; k < plen; k++) {
+            const uint32_t node = c < j ? p[k] : p[plen - 1 - k];
+            if (cyc) {
+                cyc[len] = node;
+                cyc_di[len] = step_drag_index(s.T, cur_node, node);
+            }
+            cur_node = node;
+            if (++len > limit) return 0;
+        }
+        // doubling edge of the event just reached
+        const uint32_t nxt = j ^ 1u;
+        const uint32_t nxt_node = cur_node ^ 1u;
+        if (nxt == i0) {
+            if (cyc) cyc_di[0] = s.T.self_drag[cur_node >> 1];
+            return len;
+        }
+        if (cyc) {
+            cyc[len] = nxt_node;
+            cyc_di[len] = s.T.self_drag[cur_node >> 1];
+        }
+        cur_node = nxt_node;
+        if (++len > limit) return 0;
+        c = nxt;
+    }
+}
+
+// Returns false when the shot has a junction (the caller then runs the general lift); true when the shot was lifted here
+// (or failed for good).
+template <class G>
+CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
+    const uint32_t M = s.M;
+    // a. junction test over the interior nodes of the paths (most paths are a single edge and have none)
+    if (g.tid == 0) {
+        s.hdr->scan_total = 0;   // number of interior nodes
+        s.hdr->lift_ncomp = 0;   // junction flag
+        s.hdr->lift_cyc_top = 0; // cycle buffer bump pointer
+        s.hdr->bcast = 0;        // total path edges
+    }
+    g.sync();
+    {
+        uint32_t interior = 0, edges = 0;
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            const uint32_t len = s.path_len[i];
+            if (len >= 2) edges += len - 1;
+            if (len > 2) interior += len - 2;
+        }
+        if (interior) cb_atomic_add(&s.hdr->scan_total, interior);
+        if (edges) cb_atomic_add(&s.hdr->bcast, edges);
+    }
+    g.sync();
+    const uint32_t ninterior = s.hdr->scan_total;
+    const uint32_t E = s.hdr->bcast + M / 2;
+    uint32_t HK = 0;
+    if (ninterior) {
+        HK = 16;
+        while (HK < 2 * ninterior) HK <<= 1;
+    }
+    g.sync();
+    if (g.tid == 0) {
+        uint8_t *mem = s.alloc((uint64_t{2} * E + 8 + HK) * 4);
+        s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
+    }
+    g.sync();
+    const uint32_t moff = s.hdr->scan_total;
+    g.sync();
+    if (!moff) return true;  // alloc flagged the overflow
+    uint32_t *cyc = (uint32_t *)(s.dyn + ((uint64_t)(moff - 1) << 4));
+    uint32_t *cyc_di = cyc + E + 4;
+    uint32_t *hkey = cyc_di + E + 4;
+    if (HK) {
+        for (uint32_t k = g.tid; k < HK; k += g.n) hkey[k] = HT_EMPTY;
+        g.sync();
+        for (uint32_t i = g.tid; i < M; i += g.n) {
+            const uint32_t len = s.path_len[i];
+            if (len <= 2) continue;
+            const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+            for (uint32_t k = 1; k + 1 < len; k++) {
+                const uint32_t node = p[k];
+                bool clash = s.node_is_event(node);
+                uint32_t h = ht_hash(node, HK);
+                while (!clash) {
+                    const uint32_t old = cb_atomic_cas(&hkey[h], HT_EMPTY, node);
+                    if (old == HT_EMPTY) break;
+                    if (old == node) clash = true;
+                    h = (h + 1) & (HK - 1);
+                }
+                if (clash) s.hdr->lift_ncomp = 1;
+            }
+        }
+        g.sync();
+        const bool junction = s.hdr->lift_ncomp != 0;
+        g.sync();
+        if (junction) return false;
+    }
+    // b. one thread per detection event: the component's smallest event walks, stores and discharges its cycle
+    for (uint32_t i = 2 * (uint32_t)g.tid; i < M; i += 2 * (uint32_t)g.n) {
+        const uint32_t len = plain_cycle_walk(s, i, nullptr, nullptr, E);
+        if (!len) {
+            // not the minimum of its component -- or a broken structure, which the minimum's own walk reports
+            if (s.partner[i] < 0) s.fail(SHOT_EULER_FAILED);
+            continue;
+        }
+        const uint32_t off = cb_atomic_add(&s.hdr->lift_cyc_top, len);
+        if (off + len > E) {
+            s.fail(SHOT_EULER_FAILED);
+            continue;
+        }
+        plain_cycle_walk(s, i, cyc + off, cyc_di + off, E);
+        bool done = false;
+        for (uint32_t c = 0; c < 4 && !done; c++) {
+            uint64_t v;
+            if (discharge_single_start(s, cyc + off, cyc_di + off, len, c, &v)) {
+                if (v) cb_atomic_xor64(&s.hdr->obs, v);
+                done = true;
+            }
+        }
+        if (!done) s.fail(SHOT_DISCHARGE_FAILED);
+    }
+    g.sync();
+    // every half-edge belongs to exactly one cycle: the cycles together hold E nodes, or some walk did not close
+    if (g.tid == 0 && !s.hdr->status && s.hdr->lift_cyc_top != E) s.fail(SHOT_EULER_FAILED);
+    g.sync();
+    return true;
+}
+
 template <class G>
 CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
 #ifdef CB_LIFT_PROF
@@ -2870,8 +3088,13 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
     pt.lap(5);
     const bool liftable = !s.hdr->status && s.M;
     g.sync();
-    if (liftable) lift_shot(s, g, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
-    else if (g.tid == 0 && p.edge_dump_len) *p.edge_dump_len = 0;
+    if (liftable) {
+        // the plain-cycle lift covers shots without junctions; the edge dump (a debugging hook) needs the general one
+        const bool plain = !p.edge_dump && !p.edge_dump_len && !(s.cfg.pad & 1u) && lift_shot_plain(s, g);
+        if (!plain) lift_shot(s, g, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
+    } else if (g.tid == 0 && p.edge_dump_len) {
+        *p.edge_dump_len = 0;
+    }
     g.sync();
     if (g.tid == 0) {
         pt.lap(6);

@@ -4,7 +4,10 @@
 // reference's std::map / std::unordered_map containers. Citations relative to /root/reference/src/chromobius.
 #include "host_compile.h"
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -1120,7 +1123,7 @@ HostTables compile_tables(const FlatDem &dem, uint32_t near_stride) {
 // =================================================================================================
 namespace {
 constexpr uint64_t CACHE_MAGIC = 0x3030324253454c42ull;  // "BLESB200"
-constexpr uint64_t CACHE_VERSION = 4;  // 4: drag table follows the reference container's visit order
+constexpr uint64_t CACHE_VERSION = 5;  // 4: drag table follows the reference container's visit order; 5: model text stored
 
 struct Writer {
     FILE *f;
@@ -1189,15 +1192,21 @@ uint64_t fnv1a(const void *p, size_t n, uint64_t h = 0xcbf29ce484222325ull) {
 }
 }  // namespace
 
-void save_tables(const HostTables &t, const std::string &path, uint64_t key) {
-    // written next to the final name and renamed, so a concurrent reader never sees half a file
-    std::string tmp = path + ".tmp." + std::to_string((unsigned long long)fnv1a(&t, sizeof(void *)) ^ (unsigned long long)(uintptr_t)&t);
+void save_tables(const HostTables &t, const std::string &path, uint64_t key, const std::string &dem_text) {
+    // written next to the final name and renamed, so a concurrent reader never sees half a file; the temporary name is
+    // unique per process and call
+    static std::atomic<unsigned long long> counter{0};
+    std::string tmp = path + ".tmp." + std::to_string((unsigned long long)getpid()) + "." + std::to_string(counter.fetch_add(1));
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return;
     Writer w{f};
     w.pod(CACHE_MAGIC);
     w.pod(CACHE_VERSION);
     w.pod(key);
+    // the model itself: a file is only ever used for the exact text it was compiled from (the 64-bit key names the file,
+    // it does not identify the model)
+    std::vector<char> text(dem_text.begin(), dem_text.end());
+    w.vec(text);
     tables_io(w, t);
     // the charge graph is nested: flatten it
     w.pod<uint64_t>(t.charge_graph.size());
@@ -1208,7 +1217,7 @@ void save_tables(const HostTables &t, const std::string &path, uint64_t key) {
     if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
 }
 
-bool load_tables(HostTables &t, const std::string &path, uint64_t key) {
+bool load_tables(HostTables &t, const std::string &path, uint64_t key, const std::string &dem_text) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
     Reader r{f};
@@ -1217,6 +1226,11 @@ bool load_tables(HostTables &t, const std::string &path, uint64_t key) {
     r.pod(version);
     r.pod(k);
     bool ok = r.ok && magic == CACHE_MAGIC && version == CACHE_VERSION && k == key;
+    if (ok) {
+        std::vector<char> text;
+        r.vec(text);
+        ok = r.ok && text.size() == dem_text.size() && memcmp(text.data(), dem_text.data(), text.size()) == 0;
+    }
     if (ok) {
         tables_io(r, t);
         r.pod(rows);
@@ -1246,12 +1260,12 @@ HostTables compile_tables_cached(const std::string &dem_text, bool *from_cache) 
     snprintf(name, sizeof(name), "/cb200_%016llx.tables", (unsigned long long)key);
     const std::string path = std::string(dir) + name;
     HostTables t;
-    if (load_tables(t, path, key)) {
+    if (load_tables(t, path, key, dem_text)) {
         if (from_cache) *from_cache = true;
         return t;
     }
     t = compile_tables(FlatDem::parse(dem_text));
-    save_tables(t, path, key);
+    save_tables(t, path, key, dem_text);
     return t;
 }
 

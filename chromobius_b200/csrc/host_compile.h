@@ -110,8 +110,8 @@ void build_near_table(HostTables &t, uint32_t near_stride);
 // hash of the DEM text, the table format version and the near-table setting; a file that fails its checks is ignored
 // and rewritten. `from_cache` (nullable) reports whether the tables were loaded.
 HostTables compile_tables_cached(const std::string &dem_text, bool *from_cache = nullptr);
-void save_tables(const HostTables &t, const std::string &path, uint64_t key);
-bool load_tables(HostTables &t, const std::string &path, uint64_t key);
+void save_tables(const HostTables &t, const std::string &path, uint64_t key, const std::string &dem_text);
+bool load_tables(HostTables &t, const std::string &path, uint64_t key, const std::string &dem_text);
 
 }  // namespace cb200
 

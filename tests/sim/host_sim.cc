@@ -98,6 +98,7 @@ int cbsim_decode(void *h, const uint8_t *dets, uint64_t num_shots, uint64_t stri
     p.cfg.found_cap = 256;
     p.cfg.max_events = 2 * s->tables.num_dets + 2;
     p.cfg.dyn_bytes = dyn_bytes;
+    if (getenv("CB200_NO_PLAIN_LIFT")) p.cfg.pad |= 1u;  // tests: always the general lift
     uint64_t bytes = arena_bytes_per_group(p.cfg, p.T.num_nodes, 1);
     s->arena.assign(bytes, 0);
     std::vector<uint8_t> shared(shared_bytes_per_group(p.cfg, p.T.num_dets, 1) + 16, 0);

@@ -244,3 +244,53 @@ def test_wide_blossom_layout(built, tmp_path):
         sim_util._lib = saved
     assert (got[2] == 0).all()
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_plain_cycle_lift_equals_general_lift_in_the_host_simulation(built, monkeypatch):
+    """lift_shot_plain (cycles straight from the pair list when the shot has no junction) against the general half-edge
+    machinery of lift_shot, on the same device code compiled for the host."""
+    from sim_util import SimDecoder
+    from reference_pins import load_circuit_shots
+    for name, n in [('superdense_color_code_d5_r20_p1000', 1500), ('color2surface_d7_phenom_r7_p100', 800),
+                    ('toric_superdense_color_code_epr_d12_r5_p1000', 800), ('midout488_color_code_d9_r33_p1000', 400)]:
+        dets = load_circuit_shots(name)[0][:n]
+        sim = SimDecoder(read_dem(name))
+        obs_a, w_a, st_a, _ = sim.decode(dets)
+        monkeypatch.setenv('CB200_NO_PLAIN_LIFT', '1')
+        obs_b, w_b, st_b, _ = sim.decode(dets)
+        monkeypatch.delenv('CB200_NO_PLAIN_LIFT')
+        assert st_a.max() == 0 and st_b.max() == 0
+        assert (obs_a == obs_b).all() and (w_a == w_b).all()
+
+
+def chain_dem(n, p=0.05):
+    """An RG repetition-code chain of n detectors (the shape of test_data/rep_code_rg_d9_transit_p10.stim's model):
+    with every detector fired, each Moebius subgraph becomes ONE matching component of n events."""
+    lines = ['error(%g) D0 L0' % p]
+    lines += ['error(%g) D%d D%d' % (p, k, k + 1) for k in range(n - 1)]
+    lines.append('error(%g) D%d' % (p, n - 1))
+    lines += ['detector(%g, 0, 0, %d) D%d' % (k + 0.5, 3 + (k % 2), k) for k in range(n)]
+    return '\n'.join(lines) + '\n'
+
+
+def all_fired(n):
+    dets = np.zeros((1, (n + 7) // 8), np.uint8)
+    for k in range(n):
+        dets[0, k >> 3] |= 1 << (k & 7)
+    return dets
+
+
+def test_component_size_limit_is_reported_not_mis_decoded(built):
+    """MAX_COMPONENT (decode_core.h): a matching component of up to 2000 events is solved exactly; beyond that the shot
+    is reported as `component_too_large` (status 6) -- a documented limit the reference does not have (its sparse blossom
+    has no dense per-component matrix). Just below the limit the answer equals the oracle's."""
+    ok_n, big_n = 1900, 2100
+    text = chain_dem(ok_n)
+    o = oracle.OracleDecoder(text)
+    o.set_matcher_mode(3)
+    o_obs, o_w = o.decode_batch(all_fired(ok_n))
+    assert o.matcher_stats()['max_component'] == ok_n
+    obs, w, st, _ = SimDecoder(text).decode(all_fired(ok_n), dyn_bytes=512 << 20)
+    assert st[0] == 0 and obs[0] == o_obs[0] and w[0] == o_w[0]
+    obs, w, st, _ = SimDecoder(chain_dem(big_n)).decode(all_fired(big_n), dyn_bytes=512 << 20)
+    assert st[0] == 6

@@ -100,3 +100,66 @@ def test_out_of_scratch_retries_give_the_same_answers(libs, monkeypatch, name, s
         assert (w == w0).all() and (pred == pred0).all()
         results[spares] = st.num_retried_shots
     assert results[True] > 0 and results[False] > 0
+
+
+@pytest.mark.parametrize('name,shots,chunk', [('midout_color_code_d9_r36_p1000', 20000, 1500),
+                                              ('superdense_color_code_d5_r20_p1000', 50000, 4096)])
+def test_streaming_host_input_gives_the_same_answers(libs, monkeypatch, name, shots, chunk):
+    """A large host batch is copied in chunks while the decode kernel already runs (decode_impl: streaming input); the
+    answers must not depend on it, also when the chunks that arrive later hold heavier shots than the first chunk the
+    arena was sized from (those take the scratch-overflow retry path)."""
+    cb, _ = libs
+    text = read_dem(name)
+    dets, _ = NumpyDemSampler(text).sample(shots, 12)
+    # light shots first, the heaviest last: the first chunk under-estimates the batch
+    order = np.argsort(np.unpackbits(dets, axis=1).sum(axis=1), kind='stable')
+    dets = np.ascontiguousarray(dets[order])
+    for k in range(1, 41):  # ... and forty shots far beyond the head room: the XOR of five heavy shots each
+        dets[-k] = dets[-k] ^ dets[-k - 50] ^ dets[-k - 100] ^ dets[-k - 150] ^ dets[-k - 200]
+    dec = cb._compile_text(text, device=0)
+    monkeypatch.setenv('CB200_NO_PIPELINE', '1')
+    pred0, w0 = dec.decode_with_integer_weights(dets)
+    monkeypatch.delenv('CB200_NO_PIPELINE')
+    monkeypatch.setenv('CB200_PIPELINE_CHUNK', str(chunk))
+    dec2 = cb._compile_text(text, device=0)
+    pred1, w1 = dec2.decode_with_integer_weights(dets)
+    assert (pred1 == pred0).all() and (w1 == w0).all()
+    assert dec2.last_stats.num_detection_events == dec.last_stats.num_detection_events
+    assert dec2.last_stats.max_events_per_shot == dec.last_stats.max_events_per_shot
+    assert dec2.last_stats.num_retried_shots > 0, 'the sorted batch should have outgrown the first chunk'
+    # strided host rows stream too
+    wide = np.zeros((shots, dets.shape[1] + 3), np.uint8)
+    wide[:, :dets.shape[1]] = dets
+    assert (dec2.predict_obs_flips_from_dets_bit_packed(wide[:, :dets.shape[1]]) == pred0).all()
+
+
+def test_plain_cycle_lift_equals_general_lift(libs, monkeypatch):
+    cb, _ = libs
+    for name, shots in [('midout_color_code_d9_r36_p1000', 20000), ('color2surface_d7_phenom_r7_p100', 20000),
+                        ('toric_superdense_color_code_epr_d12_r5_p1000', 8000)]:
+        text = read_dem(name)
+        dets, _ = NumpyDemSampler(text).sample(shots, 8)
+        a = cb._compile_text(text, device=0).decode_with_integer_weights(dets)
+        monkeypatch.setenv('CB200_NO_PLAIN_LIFT', '1')
+        b = cb._compile_text(text, device=0).decode_with_integer_weights(dets)
+        monkeypatch.delenv('CB200_NO_PLAIN_LIFT')
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_component_size_limit_on_the_gpu(libs):
+    """The giant-component shots of tests/test_decode_path_cpu.py through the CUDA path: 1900 events in one component
+    decode to the oracle's answer (after the scratch retries enlarge the dense blossom's memory); 2100 fail the call
+    with the documented message instead of returning a wrong answer."""
+    from test_decode_path_cpu import all_fired, chain_dem
+    cb, oracle = libs
+    text = chain_dem(1900)
+    dec = cb._compile_text(text, device=0)
+    pred, w = dec.decode_with_integer_weights(all_fired(1900))
+    od = oracle.OracleDecoder(text)
+    od.set_matcher_mode(3)
+    o_obs, o_w = od.decode_batch(all_fired(1900))
+    assert w[0] == o_w[0] and masks(pred)[0] == o_obs[0]
+    dec2 = cb._compile_text(chain_dem(2100), device=0)
+    with pytest.raises(ValueError, match='exceeded the supported size'):
+        dec2.predict_obs_flips_from_dets_bit_packed(all_fired(2100))
+    assert dec2.last_stats.first_failed_status == 6

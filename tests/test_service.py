@@ -101,3 +101,25 @@ def test_service_on_gpu_matches_local_decoder(built, tmp_path):
     finally:
         svc._stop.set()
         thread.join(timeout=5)
+
+
+def test_service_refuses_unsafe_socket_locations(tmp_path):
+    """The socket may only live in a directory other users cannot write, and a non-socket at the address is never removed
+    (the wire format itself is raw length-prefixed frames: nothing a peer sends is unpickled or evaluated)."""
+    import stat
+    from chromobius_b200 import service
+    shared = tmp_path / 'shared'
+    shared.mkdir()
+    os.chmod(shared, 0o777)
+    with pytest.raises(PermissionError):
+        service.DecoderService(str(shared / 'svc.sock'), compile_fn=_OracleBacked)
+    private = tmp_path / 'private'
+    private.mkdir(mode=0o700)
+    victim = private / 'data.txt'
+    victim.write_text('keep me')
+    with pytest.raises(FileExistsError):
+        service.DecoderService(str(victim), compile_fn=_OracleBacked)
+    assert victim.read_text() == 'keep me'
+    svc = service.DecoderService(str(private / 'svc.sock'), compile_fn=_OracleBacked)
+    assert stat.S_IMODE(os.stat(str(private / 'svc.sock')).st_mode) == 0o600
+    svc._sock.close()
