@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -285,6 +288,7 @@ struct cb200_decoder {
     // device tables (one allocation, see upload_tables)
     DeviceBuf<uint8_t> d_tables;
     size_t l2_window_bytes = 0;
+    size_t l2_persist_want = 0;          // this decoder's share of the device's persisting-L2 set-aside (0: none)
     uint32_t tune_groups_per_sm = 0;
     TablesView dview{};
     uint64_t table_bytes = 0;
@@ -309,6 +313,41 @@ struct cb200_decoder {
 };
 
 namespace {
+
+// The persisting-L2 set-aside is a per-DEVICE limit, while several decoders can live on one GPU (the sinter service
+// caches one per model; a multi-GPU handle may list a device twice): it is kept at the largest request among the live
+// decoders of that device and handed back (limit 0, persisting lines reset) when the last of them is freed.
+struct L2SetAside {
+    std::mutex mu;
+    std::map<int, std::multiset<size_t>> wants;  // device -> requests of the live decoders
+};
+L2SetAside &l2_registry() {
+    static L2SetAside r;
+    return r;
+}
+bool l2_set_aside_register(int device, size_t want) {
+    L2SetAside &r = l2_registry();
+    std::lock_guard<std::mutex> lock(r.mu);
+    auto &set = r.wants[device];
+    set.insert(want);
+    return cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, *set.rbegin()) == cudaSuccess;
+}
+void l2_set_aside_release(int device, size_t want) {
+    L2SetAside &r = l2_registry();
+    std::lock_guard<std::mutex> lock(r.mu);
+    auto it = r.wants.find(device);
+    if (it == r.wants.end()) return;
+    auto pos = it->second.find(want);
+    if (pos != it->second.end()) it->second.erase(pos);
+    if (it->second.empty()) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        r.wants.erase(it);
+    } else {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, *it->second.rbegin());
+    }
+    cudaGetLastError();
+}
 
 // All read-only tables live in ONE allocation so that a single L2 access-policy window can pin them: the matcher
 // graph is re-read by every ball of every shot, while the per-shot scratch streams through L2 behind it.
@@ -371,7 +410,8 @@ void upload_tables(cb200_decoder *d) {
     if (max_persist > 0 && max_window > 0 && hot > 0) {
         total = hot;
         size_t want = std::min<size_t>(total, (size_t)max_persist);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        d->l2_persist_want = want;
+        if (l2_set_aside_register(d->device, want)) {
             cudaStreamAttrValue attr{};
             attr.accessPolicyWindow.base_ptr = base;
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(total, (size_t)max_window);
@@ -871,6 +911,7 @@ void cb200_free(cb200_decoder *d) {
         cudaSetDevice(d->device);
         cudaStreamSynchronize(d->stream);
     }
+    if (d->l2_persist_want) l2_set_aside_release(d->device, d->l2_persist_want);
     d->d_tables.release();
     d->d_dets.release(); d->d_obs_bytes.release(); for (auto &a : d->arenas) a.buf.release(); d->d_obs64.release(); d->d_wint.release();
     d->d_wint_out.release(); d->d_edges.release(); d->d_status.release(); d->d_rounds.release(); d->d_counts.release();

@@ -55,6 +55,12 @@ const char *cb200_last_error(void);
  * Replaces Decoder::from_dem (decode/decoder.cc:24-69) as reached from CompiledDecoder::from_dem
  * (pybind/chromobius.pybind.cc:32-47), which also hands the DEM over as text. */
 int cb200_compile(const char *dem_text, int device, cb200_decoder **out);
+/* Models the reference accepts and this library rejects with CB200_ERR_INVALID_ARGUMENT (the reference hands them to
+ * PyMatching, which flips negative-weight edges and tolerates zero weights):
+ *   - a Moebius error with probability above 0.5 (negative edge weight), and
+ *   - an edge whose discretised weight rounds to 0 (p = 0.5, or a weight below 2^-24 of the largest one).
+ * Other limits: at most 64 observables (as the reference), at most 2^24 Moebius nodes, and matching components of at
+ * most 2000 detection events per shot (a larger one fails the call with CB200_ERR_DECODE, status 6). */
 
 /* Releases host and device memory. */
 void cb200_free(cb200_decoder *dec);

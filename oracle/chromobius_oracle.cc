@@ -1323,7 +1323,11 @@ struct Decoder {
     // Open ball around one event (truncated Dijkstra). radius >= 0: every node strictly closer than radius. radius < 0:
     // until more than `need_more_than` other events have been settled; the radius is the distance of the last one, and
     // every event strictly closer than it has been reported. Returns the radius (-1 when nothing more is reachable).
-    int64_t ball(node_t src, int64_t radius, size_t need_more_than, std::vector<std::pair<int, int64_t>> *found) {
+    // `extra` (open-ended searches only): keep going until `extra` events beyond the required one have been settled, if
+    // the graph has them; a search that exhausts the graph after the required event returns R_UNBOUNDED (everything
+    // reachable has been seen).
+    static constexpr int64_t R_UNBOUNDED = INT64_MAX / 4;
+    int64_t ball(node_t src, int64_t radius, size_t need_more_than, std::vector<std::pair<int, int64_t>> *found, size_t extra = 0) {
         ReusableHeap &pq = heap_buf;
         pq.clear();
         touched.clear();
@@ -1339,7 +1343,7 @@ struct Decoder {
             if (limit >= 0 && d >= limit) break;  // open ball: every event strictly closer than the radius is known
             if (u != src && event_index[u] >= 0) {
                 found->push_back({event_index[u], d});
-                if (limit < 0 && found->size() > need_more_than) {
+                if (limit < 0 && found->size() > need_more_than + extra) {
                     limit = d;
                     break;
                 }
@@ -1356,6 +1360,7 @@ struct Decoder {
             }
         }
         for (auto v : touched) dist[v] = -1;
+        if (limit < 0 && found->size() > need_more_than) limit = R_UNBOUNDED;
         return limit;
     }
 
@@ -1699,8 +1704,11 @@ struct Decoder {
                 }
             }
             if (grow.empty()) break;
+            // An open-ended request (odd component, exposed vertex) asks for ONE event more than it needs: 20 % fewer
+            // matcher rounds at d25 r100 (4.49 -> 3.60 per shot) for slightly larger components (GROW_EXTRA_EVENTS in
+            // the kernels' grow_some).
             for (auto &[i, to] : grow) {
-                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i]);
+                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i], to < 0 ? 1 : 0);
                 if (R[i] < 0) {
                     ok = false;
                     break;

@@ -117,3 +117,14 @@ def test_predict_argument_validation():
     out, w = dec.predict_weighted_obs_flips_from_dets_bit_packed(np.zeros(3, np.uint8))  # 1-D: outputs lose the shot axis
     assert out.shape == (1,) and w.shape == ()
     assert fake.calls == 3
+
+
+def test_models_the_reference_accepts_and_this_library_rejects_are_reported(built):
+    """include/chromobius_b200.h documents them: probabilities above 0.5 and zero-weight edges (PyMatching handles both)."""
+    from sim_util import SimDecoder
+    coords = 'detector(0,0,0,0) D0\ndetector(0,0,0,1) D1\n'
+    with pytest.raises(ValueError, match='above 0.5'):
+        SimDecoder('error(0.6) D0 D1\n' + coords)
+    with pytest.raises(ValueError, match='non-positive weight'):
+        SimDecoder('error(0.5) D0 D1\n' + coords)
+    SimDecoder('error(0.4) D0 D1\n' + coords)
