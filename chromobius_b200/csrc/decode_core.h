@@ -72,7 +72,10 @@ constexpr uint32_t NARROW_COMPONENT = CB_NARROW_COMPONENT;  // up to here the bl
 constexpr uint32_t MAX_ROUNDS = 64;
 // An open-ended growth request (odd component, exposed vertex) asks for this many events beyond the one it needs: one extra
 // event per request means 20 % fewer matcher rounds at d25 r100 (4.49 -> 3.60 per shot) for slightly larger components.
-constexpr uint32_t GROW_EXTRA_EVENTS = 1;
+#ifndef CB_GROW_EXTRA
+#define CB_GROW_EXTRA 1
+#endif
+constexpr uint32_t GROW_EXTRA_EVENTS = CB_GROW_EXTRA;
 // Radius of a ball that has seen everything reachable (an open-ended search that ran out of graph after its required event).
 constexpr int64_t R_UNBOUNDED = INT64_MAX / 4;
 constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;

@@ -58,6 +58,7 @@ def lib():
         L.orc_set_matcher_mode.argtypes = [vp, ctypes.c_int]
         L.orc_matcher_stats.argtypes = [vp, vp, ctypes.c_int]
         L.orc_set_odd_policy.argtypes = [vp, ctypes.c_int]
+        L.orc_set_growth_extra.argtypes = [vp, ctypes.c_int]
         L.orc_match_events.restype = i64
         L.orc_match_events.argtypes = [vp, vp, u64, vp, vp]
         _lib = L
@@ -88,6 +89,12 @@ class OracleDecoder:
         """0: dense all-pairs matcher up to 160 events, certified-local (lazy merging) beyond; 1: certified-local with eager
         merging; 2: always dense; 3: always certified-local with lazy merging (the algorithm the kernels run)."""
         lib().orc_set_matcher_mode(self._h, int(mode))
+
+    def set_growth_extra(self, extra):
+        """Events an open-ended growth request of the certified-local matcher asks for beyond the one it needs. 1 (default)
+        is what the kernels do (fewer matcher rounds); 0 is faster on a CPU. Weights are exact either way; among
+        equal-weight matchings the choice can differ."""
+        lib().orc_set_growth_extra(self._h, int(extra))
 
     def set_odd_policy(self, policy):
         lib().orc_set_odd_policy(self._h, int(policy))

@@ -1146,6 +1146,8 @@ struct Decoder {
     // merging; 2 = always dense; 3 = always certified-local with lazy merging (the kernels' algorithm)
     int matcher_mode = 0;
     int odd_policy = 0;  // 0: every member of an odd component grows; 1: only the vertices a maximum matching leaves exposed
+    int growth_extra = 1;  // events an open-ended growth request asks for beyond the required one (kernels: GROW_EXTRA_EVENTS = 1;
+                           // 0 is the cheaper setting on a CPU, where matcher rounds cost little: bench.py's CPU legs use it)
     DenseBlossom local_blossom;
     std::vector<int> loc_buf;
 
@@ -1708,7 +1710,7 @@ struct Decoder {
             // matcher rounds at d25 r100 (4.49 -> 3.60 per shot) for slightly larger components (GROW_EXTRA_EVENTS in
             // the kernels' grow_some).
             for (auto &[i, to] : grow) {
-                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i], to < 0 ? 1 : 0);
+                R[i] = ball((node_t)events[i], to, nb[i].size(), &nb[i], to < 0 ? (size_t)growth_extra : 0);
                 if (R[i] < 0) {
                     ok = false;
                     break;
@@ -1980,6 +1982,7 @@ uint64_t orc_drag_ambiguities(void *h) { return ((Decoder *)h)->t->drag_ambiguit
 uint64_t orc_radius_retries(void *h) { return ((Decoder *)h)->stat_radius_retries; }
 void orc_set_matcher_mode(void *h, int mode) { ((Decoder *)h)->matcher_mode = mode; }
 void orc_set_odd_policy(void *h, int p) { ((Decoder *)h)->odd_policy = p; }
+void orc_set_growth_extra(void *h, int k) { ((Decoder *)h)->growth_extra = k < 0 ? 0 : k; }
 void orc_matcher_stats(void *h, uint64_t *out6 /* 7 values */, int reset) {
     auto *d = (Decoder *)h;
     for (int k = 0; k < 4; k++) out6[k] = d->stat_blossoms[k];
