@@ -2034,7 +2034,9 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
         if (s.prof) {
             int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
             cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
+#ifndef CB_XPROF2
             cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
+#endif
         }
         if (bl.broken) pairs = NO_INDEX;
     } else if (bl.is_par()) {
@@ -2144,6 +2146,12 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         // The union-find persists across rounds: every union ever made stays valid (a solved component stays whole, an
         // unsolved one re-joins everything it has seen), so a round only adds unions. What the previous round's dirty
         // components used is reset here; everything else below touches all events in three passes only.
+#ifdef CB_XPROF2
+        unsigned long long xt2 = cb_clock();
+#define CB_XLAP2(slot) if (s.prof && g.tid == 0) { unsigned long long now_ = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[slot], now_ - xt2); xt2 = now_; }
+#else
+#define CB_XLAP2(slot)
+#endif
         const uint32_t prev_ncomp = s.hdr->ncomp;
         for (uint32_t c = g.tid; c < prev_ncomp; c += g.n) {
             const uint32_t r = s.comp_root[c];
@@ -2175,6 +2183,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             }
         }
         g.sync();
+        CB_XLAP2(12)
         for (uint32_t i = g.tid; i < M; i += g.n) {
             uint32_t r = uf_find(s.uf, i);
             s.root[i] = r;
@@ -2185,12 +2194,14 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             if (!s.solved[i] || s.stale[s.pc[i]] || !s.solved[r] || s.pc[r] != s.pc[i]) s.comp_dirty[r] = 1;
         }
         g.sync();
+        CB_XLAP2(13)
         for (uint32_t i = g.tid; i < M; i += g.n)
             if (s.comp_dirty[s.root[i]]) {
                 cb_atomic_add(&s.cnt[s.root[i]], 1);
                 act[cb_atomic_add(&s.hdr->nhuge, 1)] = i;
             }
         g.sync();
+        CB_XLAP2(14)
         const uint32_t nact = s.hdr->nhuge;
         for (uint32_t k = g.tid; k < nact; k += g.n) {
             const uint32_t i = act[k];
@@ -2213,6 +2224,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             if (s.solved[i]) s.stale[s.pc[i]] = 0;
         }
         g.sync();
+        CB_XLAP2(15)
         const uint32_t ncomp = s.hdr->ncomp;
         pt.lap(2);
         // small components: one thread each; the rest is queued for the blossom
@@ -2787,46 +2799,56 @@ CB_HD uint32_t step_drag_index(const TablesView &T, uint32_t a, uint32_t b) {
     return he != NO_INDEX ? T.adj_drag[he] : NO_INDEX;
 }
 
-// Walks the cycle that starts at event i0 (an even event index). Returns the number of cycle nodes, or 0 when a
-// smaller event index turned up (i0 is not the component's minimum) or the walk did not close. With `cyc` set, also
-// stores the nodes and the drag index of the step that arrives at each of them (cyc_di[0] belongs to the closing step).
-CB_HDN uint32_t plain_cycle_walk(Shot &s, uint32_t i0, uint32_t *cyc, uint32_t *cyc_di, uint32_t limit) {
-    uint32_t len = 1;
-    uint32_t cur_node = s.event_node(i0);
-    if (cyc) cyc[0] = cur_node;
+// Length (number of nodes) of the cycle that starts at event i0 (an even event index), or 0 when a smaller event index
+// turns up (i0 is not the component's minimum) or the walk does not close within `limit` nodes. Follows the partner
+// links only -- one dependent load per event, no path is read.
+CB_HDN uint32_t plain_cycle_length(Shot &s, uint32_t i0, uint32_t limit) {
+    uint32_t len = 0;
     uint32_t c = i0;
     while (true) {
         const int32_t pj = s.partner[c];
         if (pj < 0) return 0;
         const uint32_t j = (uint32_t)pj;
         if (j < i0 || (j ^ 1u) < i0) return 0;
+        const uint32_t plen = s.path_len[c < j ? c : j];
+        if (plen < 2) return 0;
+        len += plen;  // plen - 1 path nodes after the current one, plus the twin reached through the doubling edge
+        if (len > limit) return 0;
+        c = j ^ 1u;
+        if (c == i0) return len;
+    }
+}
+
+// Stores the cycle that starts at event i0 (the minimum of its component, `len` nodes as counted above): the nodes and,
+// for each, the drag index of the step that arrives at it (cyc_di[0] belongs to the closing step).
+CB_HDN void plain_cycle_fill(Shot &s, uint32_t i0, uint32_t *cyc, uint32_t *cyc_di, uint32_t len) {
+    uint32_t at = 1;
+    uint32_t cur_node = s.event_node(i0);
+    cyc[0] = cur_node;
+    uint32_t c = i0;
+    while (at <= len) {
+        const uint32_t j = (uint32_t)s.partner[c];
         const uint32_t owner = c < j ? c : j;
         const uint32_t plen = s.path_len[owner];
-        if (plen < 2) return 0;
         const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[owner] << 4));
         for (uint32_t k = 1; k < plen; k++) {
             const uint32_t node = c < j ? p[k] : p[plen - 1 - k];
-            if (cyc) {
-                cyc[len] = node;
-                cyc_di[len] = step_drag_index(s.T, cur_node, node);
-            }
+            cyc[at] = node;
+            cyc_di[at] = step_drag_index(s.T, cur_node, node);
             cur_node = node;
-            if (++len > limit) return 0;
+            at++;
         }
         // doubling edge of the event just reached
-        const uint32_t nxt = j ^ 1u;
-        const uint32_t nxt_node = cur_node ^ 1u;
-        if (nxt == i0) {
-            if (cyc) cyc_di[0] = s.T.self_drag[cur_node >> 1];
-            return len;
+        const uint32_t di = s.T.self_drag[cur_node >> 1];
+        c = j ^ 1u;
+        if (c == i0) {
+            cyc_di[0] = di;
+            return;
         }
-        if (cyc) {
-            cyc[len] = nxt_node;
-            cyc_di[len] = s.T.self_drag[cur_node >> 1];
-        }
-        cur_node = nxt_node;
-        if (++len > limit) return 0;
-        c = nxt;
+        cur_node ^= 1u;
+        cyc[at] = cur_node;
+        cyc_di[at] = di;
+        at++;
     }
 }
 
@@ -2900,7 +2922,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     }
     // b. one thread per detection event: the component's smallest event walks, stores and discharges its cycle
     for (uint32_t i = 2 * (uint32_t)g.tid; i < M; i += 2 * (uint32_t)g.n) {
-        const uint32_t len = plain_cycle_walk(s, i, nullptr, nullptr, E);
+        const uint32_t len = plain_cycle_length(s, i, E);
         if (!len) {
             // not the minimum of its component -- or a broken structure, which the minimum's own walk reports
             if (s.partner[i] < 0) s.fail(SHOT_EULER_FAILED);
@@ -2911,7 +2933,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
             s.fail(SHOT_EULER_FAILED);
             continue;
         }
-        plain_cycle_walk(s, i, cyc + off, cyc_di + off, E);
+        plain_cycle_fill(s, i, cyc + off, cyc_di + off, len);
         bool done = false;
         for (uint32_t c = 0; c < 4 && !done; c++) {
             uint64_t v;
