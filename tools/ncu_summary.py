@@ -45,6 +45,15 @@ with open(out_txt, 'w') as f:
     f.write(funcs)
 dram = to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
 with open(out_json, 'w') as f:
+    def num(name):
+        try:
+            return float(metric[name][0])
+        except Exception:
+            return None
     json.dump({'dram_bytes_per_launch': dram, 'shots_per_launch': shots_per_launch, 'kernel': kernel, 'capture': desc,
+               'issue_active_pct': num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+               'warps_active_pct': num('sm__warps_active.avg.pct_of_peak_sustained_active'),
+               'l2_hit_pct': num('lts__t_sector_hit_rate.pct'), 'l1_hit_pct': num('l1tex__t_sector_hit_rate.pct'),
+               'threads_per_warp_instruction': num('smsp__thread_inst_executed_per_inst_executed.ratio'),
                'gpu_time_ms_under_ncu': float(metric['gpu__time_duration.sum'][0]) * {'ns': 1e-6, 'us': 1e-3, 'ms': 1, 's': 1e3}.get(metric['gpu__time_duration.sum'][1], 1)}, f, indent=1)
 print(open(out_txt).read()[:3000])
