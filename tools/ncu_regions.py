@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Stall-reason mix of an ncu report per code region of decode_core.h (line ranges below; needs -lineinfo).
 
-usage: ncu_regions.py report.ncu-rep
+usage: ncu_regions.py report.ncu-rep [decode_core.h]
 """
 import collections, csv, io, subprocess, sys
 rep = sys.argv[1]
@@ -25,7 +25,19 @@ for row in csv.reader(io.StringIO(text)):
     c['samples']+=num('# Samples'); c['inst']+=num('Instructions Executed')
     for h in hdr:
         if h.startswith('stall_') and 'Not Issued' not in h: c[h]+=num(h)
-ranges={'blossom struct (1006-1700)':(1006,1700),'solve_component_* / fill / writeback (1700-1965)':(1700,1965),'match_shot (1990-2200)':(1990,2200),'explore/ball (530-1000)':(530,1000),'paths (2200-2450)':(2200,2450),'lift (2450-2830)':(2450,2830)}
+# Region boundaries are found from the source itself (function names), so they follow the code as it moves.
+import re
+src_path = sys.argv[2] if len(sys.argv) > 2 else 'chromobius_b200/csrc/decode_core.h'
+src_lines = open(src_path).read().split('\n')
+def line_of(pattern):
+    for k, ln in enumerate(src_lines):
+        if re.search(pattern, ln):
+            return k + 1
+    raise SystemExit('pattern not found: ' + pattern)
+marks = [('ingest / explore / ball', r'void ingest_shot\('), ('blossom struct', r'^struct Blossom \{'), ('union-find / solve_component_* / fill / writeback', r'uint32_t uf_find\('),
+         ('grow_some', r'void grow_some\('), ('match_shot (rounds, waves)', r'uint32_t match_shot\('), ('paths', r'bool near_path_emit\('), ('lift + discharge', r'^struct OptMask')]
+bounds = [(name, line_of(pat)) for name, pat in marks] + [('end', len(src_lines) + 1)]
+ranges = {'%s (%d-%d)' % (bounds[k][0], bounds[k][1], bounds[k + 1][1]): (bounds[k][1], bounds[k + 1][1]) for k in range(len(marks))}
 tot=sum(c['samples'] for c in per.values())
 for name,(a,b) in ranges.items():
     agg=collections.Counter()
