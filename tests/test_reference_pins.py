@@ -44,7 +44,8 @@ def test_container_visit_order_restatement_matches_libstdcxx():
         assert (_visit_order(keys, 0) == _visit_order(keys, 1)).all(), (trial, n)
 
 
-@pytest.mark.parametrize('name', [n for n, _ in PINS] + ['fix_check_1', 'hard_config'])
+@pytest.mark.parametrize('name', [n for n, _ in PINS] + ['fix_check_1', 'hard_config', 'detector_reorder_superdense_round',
+                                                         'detector_unreorder_superdense_round'])
 def test_product_tables_equal_oracle_tables(name):
     """describe_decoder dumps (charge graph, rgb reps, every drag entry, Moebius DEM) of the two compile steps agree,
     in particular on the circuits where the drag table depends on the container's visit order."""
