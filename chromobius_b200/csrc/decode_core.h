@@ -1823,69 +1823,137 @@ CB_HD void request_growth(Shot &s, uint32_t ev, int64_t to) {
 //     2 (d_ab + d_cd - d_bd) <= t + s <= 2 d_ac      and      2 (d_ab - d_bc) <= t - s <= 2 (d_ad - d_cd),
 // a non-empty box by optimality. The balanced point (d_ab, d_cd) is clamped into it. Returns false (generic solver)
 // when the seen edges admit no perfect matching.
+// The six distances live in named scalars and the three pairings are spelled out: indexing a 4 x 4 local array with
+// run-time indices made the compiler build select trees over every element (27 KB of code for this routine, run by
+// divergent single threads).
 CB_HDN bool solve_component_four(Shot &s, const uint32_t *mem) {
-    int64_t d[4][4];
-    for (int a = 0; a < 4; a++)
-        for (int b = 0; b < 4; b++) d[a][b] = -1;
-    for (int a = 0; a < 4; a++) {
-        const NbEntry *l = nb_list(s, mem[a]);
-        for (uint32_t k = 0; k < s.nb_cnt[mem[a]]; k++)
-            for (int b = 0; b < 4; b++)
-                if (l[k].ev == mem[b]) d[a][b] = d[b][a] = l[k].d;
+    const uint32_t e0 = mem[0], e1 = mem[1], e2 = mem[2], e3 = mem[3];
+    int64_t d01 = -1, d02 = -1, d03 = -1, d12 = -1, d13 = -1, d23 = -1;
+    {
+        const NbEntry *l = nb_list(s, e0);
+        const uint32_t n = s.nb_cnt[e0];
+        CB_LOOP
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t ev = l[k].ev;
+            if (ev == e1) d01 = l[k].d;
+            else if (ev == e2) d02 = l[k].d;
+            else if (ev == e3) d03 = l[k].d;
+        }
     }
-    // pairings in fixed preference order: {01,23}, {02,13}, {03,12}
-    const int pa[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
+    {
+        const NbEntry *l = nb_list(s, e1);
+        const uint32_t n = s.nb_cnt[e1];
+        CB_LOOP
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t ev = l[k].ev;
+            if (ev == e0) d01 = l[k].d;
+            else if (ev == e2) d12 = l[k].d;
+            else if (ev == e3) d13 = l[k].d;
+        }
+    }
+    {
+        const NbEntry *l = nb_list(s, e2);
+        const uint32_t n = s.nb_cnt[e2];
+        CB_LOOP
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t ev = l[k].ev;
+            if (ev == e0) d02 = l[k].d;
+            else if (ev == e1) d12 = l[k].d;
+            else if (ev == e3) d23 = l[k].d;
+        }
+    }
+    {
+        const NbEntry *l = nb_list(s, e3);
+        const uint32_t n = s.nb_cnt[e3];
+        CB_LOOP
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t ev = l[k].ev;
+            if (ev == e0) d03 = l[k].d;
+            else if (ev == e1) d13 = l[k].d;
+            else if (ev == e2) d23 = l[k].d;
+        }
+    }
+    // pairings in fixed preference order: {01,23}, {02,13}, {03,12}; the first cheapest one wins
     int best = -1;
     int64_t best_cost = 0;
-    for (int k = 0; k < 3; k++) {
-        int64_t x = d[pa[k][0]][pa[k][1]], y = d[pa[k][2]][pa[k][3]];
-        if (x < 0 || y < 0) continue;
-        if (best < 0 || x + y < best_cost) {
-            best = k;
-            best_cost = x + y;
-        }
+    if (d01 >= 0 && d23 >= 0) {
+        best = 0;
+        best_cost = d01 + d23;
+    }
+    if (d02 >= 0 && d13 >= 0 && (best < 0 || d02 + d13 < best_cost)) {
+        best = 1;
+        best_cost = d02 + d13;
+    }
+    if (d03 >= 0 && d12 >= 0 && (best < 0 || d03 + d12 < best_cost)) {
+        best = 2;
+        best_cost = d03 + d12;
     }
     if (best < 0) {
         // No pairing has both edges: the seen edges form a star (the only connected graph on four vertices without a
         // perfect matching). The blossom's greedy start pairs the centre with its closest leaf (lowest index on ties) and
         // no augmenting path exists afterwards, so the other two leaves are left over and look further.
         int c = -1;
-        for (int a = 0; a < 4 && c < 0; a++) {
-            int deg = 0;
-            for (int b = 0; b < 4; b++) deg += d[a][b] >= 0;
-            if (deg == 3) c = a;
-        }
+        int64_t x0 = 0, x1 = 0, x2 = 0;  // distances from the centre to the other three vertices, in index order
+        if (d01 >= 0 && d02 >= 0 && d03 >= 0) { c = 0; x0 = d01; x1 = d02; x2 = d03; }
+        else if (d01 >= 0 && d12 >= 0 && d13 >= 0) { c = 1; x0 = d01; x1 = d12; x2 = d13; }
+        else if (d02 >= 0 && d12 >= 0 && d23 >= 0) { c = 2; x0 = d02; x1 = d12; x2 = d23; }
+        else if (d03 >= 0 && d13 >= 0 && d23 >= 0) { c = 3; x0 = d03; x1 = d13; x2 = d23; }
         if (c < 0) return false;
-        int leaf = -1;
-        for (int b = 0; b < 4; b++)
-            if (b != c && (leaf < 0 || d[c][b] < d[c][leaf])) leaf = b;
-        for (int b = 0; b < 4; b++) {
-            s.solved[mem[b]] = 0;
-            if (b != c && b != leaf) request_growth(s, mem[b], -1);
-        }
+        int leaf_pos = 0;  // position among the three non-centre vertices (ascending index); first minimum
+        int64_t leaf_d = x0;
+        if (x1 < leaf_d) { leaf_pos = 1; leaf_d = x1; }
+        if (x2 < leaf_d) { leaf_pos = 2; leaf_d = x2; }
+        const int leaf = leaf_pos + (leaf_pos >= c ? 1 : 0);
+        s.solved[e0] = 0;
+        if (c != 0 && leaf != 0) request_growth(s, e0, -1);
+        s.solved[e1] = 0;
+        if (c != 1 && leaf != 1) request_growth(s, e1, -1);
+        s.solved[e2] = 0;
+        if (c != 2 && leaf != 2) request_growth(s, e2, -1);
+        s.solved[e3] = 0;
+        if (c != 3 && leaf != 3) request_growth(s, e3, -1);
         return true;
     }
-    const int A = pa[best][0], B = pa[best][1], C = pa[best][2], D = pa[best][3];
-    const int64_t dab = d[A][B], dcd = d[C][D];
-    int64_t P = dab + dcd, Q = dab - dcd;
-    if (d[A][C] >= 0 && P > 2 * d[A][C]) P = 2 * d[A][C];
-    if (d[B][D] >= 0 && P < 2 * (dab + dcd - d[B][D])) P = 2 * (dab + dcd - d[B][D]);
-    if (d[A][D] >= 0 && Q > 2 * (d[A][D] - dcd)) Q = 2 * (d[A][D] - dcd);
-    if (d[B][C] >= 0 && Q < 2 * (dab - d[B][C])) Q = 2 * (dab - d[B][C]);
-    const int64_t t = (P + Q) / 2, u = (P - Q) / 2;
-    const int64_t h[4] = {t, 2 * dab - t, u, 2 * dcd - u};
-    const int who[4] = {A, B, C, D};
-    for (int k = 0; k < 4; k++) {
-        uint32_t e = mem[who[k]];
-        s.h[e] = h[k];
-        s.solved[e] = 1;
-        s.pc[e] = mem[0];
-        if (h[k] > s.R[e]) request_growth(s, e, h[k]);
+    // (A, B, C, D) = (0,1,2,3), (0,2,1,3) or (0,3,1,2)
+    uint32_t eB, eC, eD;
+    int64_t dab, dcd, dac, dbd, dad, dbc;
+    if (best == 0) {
+        eB = e1; eC = e2; eD = e3;
+        dab = d01; dcd = d23; dac = d02; dbd = d13; dad = d03; dbc = d12;
+    } else if (best == 1) {
+        eB = e2; eC = e1; eD = e3;
+        dab = d02; dcd = d13; dac = d01; dbd = d23; dad = d03; dbc = d12;
+    } else {
+        eB = e3; eC = e1; eD = e2;
+        dab = d03; dcd = d12; dac = d01; dbd = d23; dad = d02; dbc = d13;
     }
-    s.partner[mem[A]] = (int32_t)mem[B];
-    s.partner[mem[B]] = (int32_t)mem[A];
-    s.partner[mem[C]] = (int32_t)mem[D];
-    s.partner[mem[D]] = (int32_t)mem[C];
+    int64_t P = dab + dcd, Q = dab - dcd;
+    if (dac >= 0 && P > 2 * dac) P = 2 * dac;
+    if (dbd >= 0 && P < 2 * (dab + dcd - dbd)) P = 2 * (dab + dcd - dbd);
+    if (dad >= 0 && Q > 2 * (dad - dcd)) Q = 2 * (dad - dcd);
+    if (dbc >= 0 && Q < 2 * (dab - dbc)) Q = 2 * (dab - dbc);
+    const int64_t t = (P + Q) / 2, u = (P - Q) / 2;
+    const int64_t hA = t, hB = 2 * dab - t, hC = u, hD = 2 * dcd - u;
+    s.h[e0] = hA;
+    s.solved[e0] = 1;
+    s.pc[e0] = e0;
+    if (hA > s.R[e0]) request_growth(s, e0, hA);
+    s.h[eB] = hB;
+    s.solved[eB] = 1;
+    s.pc[eB] = e0;
+    if (hB > s.R[eB]) request_growth(s, eB, hB);
+    s.h[eC] = hC;
+    s.solved[eC] = 1;
+    s.pc[eC] = e0;
+    if (hC > s.R[eC]) request_growth(s, eC, hC);
+    s.h[eD] = hD;
+    s.solved[eD] = 1;
+    s.pc[eD] = e0;
+    if (hD > s.R[eD]) request_growth(s, eD, hD);
+    s.partner[e0] = (int32_t)eB;
+    s.partner[eB] = (int32_t)e0;
+    s.partner[eC] = (int32_t)eD;
+    s.partner[eD] = (int32_t)eC;
     return true;
 }
 
