@@ -904,6 +904,7 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
     uint32_t nfound = 0, end_pos = 0;  // entries [0, end_pos) take part
     int64_t limit = radius;
     bool decided = false;
+    CB_LOOP
     for (uint32_t pos = 0; pos < stride && !decided; pos += lanes) {
         const NearEntry e = *near_at(s.T, src, pos + lane);
         const bool pad = e.dist_flag == NEAR_PAD;
@@ -953,6 +954,7 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
     if (!off) return true;  // alloc flagged the overflow
     NbEntry *dst = (NbEntry *)(s.dyn + (off - 1));
     uint32_t run = 0;
+    CB_LOOP
     for (uint32_t pos = 0; pos < end_pos; pos += lanes) {
         const uint32_t p = pos + lane;
         bool is_ev = false;
@@ -1964,9 +1966,11 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
     // deterministic member order: insertion sort (components are small)
+    CB_LOOP
     for (uint32_t a = 1; a < n; a++) {
         uint32_t v = mem[a];
         uint32_t b = a;
+        CB_LOOP
         while (b > 0 && mem[b - 1] > v) {
             mem[b] = mem[b - 1];
             b--;
@@ -1975,6 +1979,7 @@ CB_HDN bool solve_component_small(Shot &s, uint32_t c) {
     }
     if (n & 1) {
         // nobody can be left over: every member looks further
+        CB_LOOP
         for (uint32_t a = 0; a < n; a++) {
             s.solved[mem[a]] = 0;
             request_growth(s, mem[a], -1);
@@ -2021,20 +2026,26 @@ CB_HD uint64_t blossom_bytes(uint32_t n) {
 template <class G>
 CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n, const uint32_t *mem, int64_t *W, uint32_t ws) {
     const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    CB_LOOP
     for (uint32_t k = lane; k < (n + 1) * ws; k += lanes) W[k] = 0;
+    CB_LOOP
     for (uint32_t a = lane; a < n; a += lanes) s.lidx[mem[a]] = a + 1;
     g.wsync();
     int64_t big = 2;
+    CB_LOOP
     for (uint32_t a = lane; a < n; a += lanes) {
         const NbEntry *l = nb_list(s, mem[a]);
         const uint32_t cnt = s.nb_cnt[mem[a]];
+        CB_LOOP
         for (uint32_t k = 0; k < cnt; k++)
             if (s.root[l[k].ev] == r && l[k].d + 2 > big) big = l[k].d + 2;
     }
     big = (int64_t)(~g.min64(~(uint64_t)big));  // maximum over the lanes
+    CB_LOOP
     for (uint32_t a = lane; a < n; a += lanes) {
         const NbEntry *l = nb_list(s, mem[a]);
         const uint32_t cnt = s.nb_cnt[mem[a]];
+        CB_LOOP
         for (uint32_t k = 0; k < cnt; k++) {
             if (s.root[l[k].ev] != r) continue;
             const uint32_t b = s.lidx[l[k].ev];
@@ -2052,6 +2063,7 @@ CB_HDN void blossom_write_back(Shot &s, const G &g, uint32_t n, const uint32_t *
                                const uint16_t *match, const int64_t *lab) {
     const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
     if (pairs * 2 != n) {
+        CB_LOOP
         for (uint32_t a = lane; a < n; a += lanes) {
             s.solved[mem[a]] = 0;
             if (!match[a + 1]) request_growth(s, mem[a], -1);
@@ -2059,6 +2071,7 @@ CB_HDN void blossom_write_back(Shot &s, const G &g, uint32_t n, const uint32_t *
         g.wsync();
         return;
     }
+    CB_LOOP
     for (uint32_t a = lane; a < n; a += lanes) {
         uint32_t e = mem[a];
         int64_t need = big - lab[a + 1];  // = 2 * y_a
