@@ -498,8 +498,10 @@ CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_
     if (lo > n) lo = n;
     if (hi > n) hi = n;
     uint32_t sum = 0;
+    CB_LOOP
     for (uint32_t k = lo; k < hi; k++) sum += arr[k];
     uint32_t incl = sum;
+    CB_LOOP
     for (int o = 1; o < g.lanes; o <<= 1) {
         uint32_t t = g.shfl32(incl, g.lane >= o ? g.lane - o : g.lane);
         if (g.lane >= o) incl += t;
@@ -507,11 +509,13 @@ CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_
     if (g.lane == g.lanes - 1) s.scan_tmp[g.warp] = incl;
     g.sync();
     uint32_t run = incl - sum, total = 0;
+    CB_LOOP
     for (int w = 0; w < g.nwarps; w++) {
         uint32_t v = s.scan_tmp[w];
         if (w < g.warp) run += v;
         total += v;
     }
+    CB_LOOP
     for (uint32_t k = lo; k < hi; k++) {
         uint32_t v = arr[k];
         arr[k] = run;
@@ -538,12 +542,14 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
         uint32_t head = (uint32_t)(((16u - (uint32_t)((uintptr_t)row & 15u)) & 15u) >> 2);
         if (head > full) head = full;
         const uint32_t body = (full - head) / 4;
+        CB_LOOP
         for (uint32_t w = g.tid; w < head; w += g.n) {
             const uint32_t v = row32[w] & mask32[w];
             s.words[w] = v;
             s.word_rank[w] = popc32(v);
         }
         const U4 *row128 = (const U4 *)(row32 + head);
+        CB_LOOP
         for (uint32_t k = g.tid; k < body; k += g.n) {
             const U4 r = row128[k];
             const uint32_t w = head + 4 * k;
@@ -557,11 +563,13 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
             s.word_rank[w + 2] = popc32(v2);
             s.word_rank[w + 3] = popc32(v3);
         }
+        CB_LOOP
         for (uint32_t w = head + 4 * body + g.tid; w < s.nwords; w += g.n) {
             uint32_t v = 0;
             if (w < full) {
                 v = row32[w] & mask32[w];
             } else {
+                CB_LOOP
                 for (uint32_t b = 0; b < 4; b++) {
                     const uint32_t k = 4 * w + b;
                     if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
@@ -571,8 +579,10 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
             s.word_rank[w] = popc32(v);
         }
     } else {
+        CB_LOOP
         for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
             uint32_t v = 0;
+            CB_LOOP
             for (uint32_t b = 0; b < 4; b++) {
                 uint32_t k = 4 * w + b;
                 if (k < nb) v |= (uint32_t)(row[k] & s.T.ingest_mask[k]) << (8 * b);
@@ -596,9 +606,11 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
         g.sync();
         return;
     }
+    CB_LOOP
     for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
         uint32_t run = s.word_rank[w];
         uint32_t v = s.words[w];
+        CB_LOOP
         while (v) {
             uint32_t b = ctz32(v);
             v &= v - 1;
@@ -2181,6 +2193,7 @@ template <class G, class PT>
 CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
     const uint32_t M = s.M;
     s.chunk_left = 0;  // the dynamic region was reset for this shot
+    CB_LOOP
     for (uint32_t i = g.tid; i < M; i += g.n) {
         s.partner[i] = -1;
         s.solved[i] = 0;
@@ -2204,9 +2217,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
     explore_first_near(s, g);
     CB_XLAP(s, g, xt, 12)
     // the few events whose row held no event: one warp each (the lanes look at 32 events at a time)
+    CB_LOOP
     for (uint32_t base = (uint32_t)g.warp * (uint32_t)g.lanes; base < M; base += (uint32_t)(g.nwarps * g.lanes)) {
         const uint32_t i = base + (uint32_t)g.lane;
         uint32_t todo = g.ballot(i < M && s.nb_cnt[i] == 0);
+        CB_LOOP
         while (todo) {
             explore_event(s, g, base + ctz32(todo), -1, 0);
             todo &= todo - 1;
@@ -2215,6 +2230,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
     CB_XLAP(s, g, xt, 13)
     uint32_t round = 0;
     uint32_t *const act = s.lidx;  // events of this round's dirty components (lidx is only used inside the blossom solves)
+    CB_LOOP
     while (true) {
         g.sync();
         pt.lap(round == 0 ? 1 : 4);
@@ -2234,6 +2250,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
 #define CB_XLAP2(slot)
 #endif
         const uint32_t prev_ncomp = s.hdr->ncomp;
+        CB_LOOP
         for (uint32_t c = g.tid; c < prev_ncomp; c += g.n) {
             const uint32_t r = s.comp_root[c];
             s.cnt[r] = 0;
@@ -2252,9 +2269,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         // Lazy merging: two events are joined when either has no dual yet or their duals overlap (h_i + h_j > 2 d).
         // A violated pair inside one solved component is either an old blossom-internal edge or a pair first seen after
         // the solve -- only a ball that grew since can show the latter, which marks it stale.
+        CB_LOOP
         for (uint32_t i = g.tid; i < M; i += g.n) {
             const bool si = s.solved[i] != 0;
             const NbEntry *l = nb_list(s, i);
+            CB_LOOP
             for (uint32_t k = 0; k < s.nb_cnt[i]; k++) {
                 uint32_t j = l[k].ev;
                 if (!si || !s.solved[j] || s.h[i] + s.h[j] > 2 * l[k].d) {
@@ -2265,6 +2284,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         }
         g.sync();
         CB_XLAP2(12)
+        CB_LOOP
         for (uint32_t i = g.tid; i < M; i += g.n) {
             uint32_t r = uf_find(s.uf, i);
             s.root[i] = r;
@@ -2276,6 +2296,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         }
         g.sync();
         CB_XLAP2(13)
+        CB_LOOP
         for (uint32_t i = g.tid; i < M; i += g.n)
             if (s.comp_dirty[s.root[i]]) {
                 cb_atomic_add(&s.cnt[s.root[i]], 1);
@@ -2284,6 +2305,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         g.sync();
         CB_XLAP2(14)
         const uint32_t nact = s.hdr->nhuge;
+        CB_LOOP
         for (uint32_t k = g.tid; k < nact; k += g.n) {
             const uint32_t i = act[k];
             if (s.root[i] == i) {
@@ -2297,6 +2319,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             }
         }
         g.sync();
+        CB_LOOP
         for (uint32_t k = g.tid; k < nact; k += g.n) {
             const uint32_t i = act[k];
             const uint32_t r = s.root[i];
@@ -2309,6 +2332,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         const uint32_t ncomp = s.hdr->ncomp;
         pt.lap(2);
         // small components: one thread each; the rest is queued for the blossom
+        CB_LOOP
         for (uint32_t c = g.tid; c < ncomp; c += g.n)
             if (!solve_component_small(s, c)) s.blist[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
@@ -2324,9 +2348,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         if (nbig) {
             // order: (size descending, root ascending), by counting predecessors -- one thread per component.
             // s.path_off (unused until the path phase) receives the ordered list, s.fillp the sizes.
+            CB_LOOP
             for (uint32_t k = (uint32_t)g.tid; k < nbig; k += (uint32_t)g.n) {
                 const uint32_t v = s.blist[k], vr = s.comp_root[v], vn = s.cnt[vr];
                 uint32_t rank = 0;
+                CB_LOOP
                 for (uint32_t j = 0; j < nbig; j++) {
                     const uint32_t ur = s.comp_root[s.blist[j]], un = s.cnt[ur];
                     rank += (un > vn || (un == vn && ur < vr)) ? 1u : 0u;
@@ -2340,6 +2366,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
                 uint32_t wave = 0;
                 uint64_t top = 0;
                 s.scan_tmp[0] = 0;  // scan_tmp[w] = first blossom of wave w
+                CB_LOOP
                 for (uint32_t k = 0; k < nbig; k++) {
                     const uint64_t need = align16(blossom_bytes<G>(s.fillp[k]));
                     if (need > pool) {
@@ -2361,9 +2388,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             const uint32_t nwaves = s.hdr->bcast;
             const uint32_t ngrow_cf = s.hdr->ngrow;  // complete: the closed-form pass ended at a barrier, no blossom has run yet
             g.sync();
+            CB_LOOP
             for (uint32_t wave = 0; wave < nwaves; wave++) {
                 const uint32_t k0 = s.scan_tmp[wave], k1 = s.scan_tmp[wave + 1];
                 // largest first, dealt out in serpentine order (warp 0 gets the 1st and the 16th, warp 7 the 8th and 9th)
+                CB_LOOP
                 for (uint32_t base = k0, pass = 0; base < k1; base += g.nwarps, pass++) {
                     const uint32_t k = base + ((pass & 1) ? (uint32_t)(g.nwarps - 1 - g.warp) : (uint32_t)g.warp);
                     if (k >= k1) continue;
@@ -2381,6 +2410,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             if (s.prof && g.tid == 0) cb_atomic_add64((uint64_t *)&s.prof[12 + (round < 4 ? round - 1 : 3)], pt.t[9] - wave_prof_before);
 #endif
             if (s.sh_ball.H)
+                CB_LOOP
                 for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
         }
         g.sync();
@@ -2948,6 +2978,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     g.sync();
     {
         uint32_t interior = 0, edges = 0;
+        CB_LOOP
         for (uint32_t i = g.tid; i < M; i += g.n) {
             const uint32_t len = s.path_len[i];
             if (len >= 2) edges += len - 1;
@@ -2962,6 +2993,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     uint32_t HK = 0;
     if (ninterior) {
         HK = 16;
+        CB_LOOP
         while (HK < 2 * ninterior) HK <<= 1;
     }
     g.sync();
@@ -2977,16 +3009,20 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     uint32_t *cyc_di = cyc + E + 4;
     uint32_t *hkey = cyc_di + E + 4;
     if (HK) {
+        CB_LOOP
         for (uint32_t k = g.tid; k < HK; k += g.n) hkey[k] = HT_EMPTY;
         g.sync();
+        CB_LOOP
         for (uint32_t i = g.tid; i < M; i += g.n) {
             const uint32_t len = s.path_len[i];
             if (len <= 2) continue;
             const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
+            CB_LOOP
             for (uint32_t k = 1; k + 1 < len; k++) {
                 const uint32_t node = p[k];
                 bool clash = s.node_is_event(node);
                 uint32_t h = ht_hash(node, HK);
+                CB_LOOP
                 while (!clash) {
                     const uint32_t old = cb_atomic_cas(&hkey[h], HT_EMPTY, node);
                     if (old == HT_EMPTY) break;
@@ -3002,6 +3038,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
         if (junction) return false;
     }
     // b. one thread per detection event: the component's smallest event walks, stores and discharges its cycle
+    CB_LOOP
     for (uint32_t i = 2 * (uint32_t)g.tid; i < M; i += 2 * (uint32_t)g.n) {
         const uint32_t len = plain_cycle_length(s, i, E);
         if (!len) {
@@ -3016,6 +3053,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
         }
         plain_cycle_fill(s, i, cyc + off, cyc_di + off, len);
         bool done = false;
+        CB_LOOP
         for (uint32_t c = 0; c < 4 && !done; c++) {
             uint64_t v;
             if (discharge_single_start(s, cyc + off, cyc_di + off, len, c, &v)) {
