@@ -43,12 +43,14 @@ struct CudaError : std::runtime_error {
 // ---------------------------------------------------------------------------------------------------------------
 template <int GROUP>
 struct DevGroup {
-    int tid;
-    int n;
-    int lane;
-    int lanes;
-    int warp;
-    int nwarps;
+    // Stateless: everything derives from threadIdx / GROUP, so passing the group by reference through non-inlined
+    // functions costs no local memory and n / lanes / nwarps are compile-time constants.
+    __device__ __forceinline__ int tid() const { return GROUP == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+    __device__ __forceinline__ constexpr int n() const { return GROUP; }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ constexpr int lanes() const { return 32; }
+    __device__ __forceinline__ int warp() const { return GROUP == 32 ? 0 : (int)(threadIdx.x >> 5); }
+    __device__ __forceinline__ constexpr int nwarps() const { return GROUP == 32 ? 1 : GROUP / 32; }
     __device__ __forceinline__ void sync() const {
         if (GROUP == 32) __syncwarp();
         else __syncthreads();
@@ -81,24 +83,30 @@ struct DevGroup {
 constexpr int WARP_MODE_BLOCK = 128;  // threads per block when GROUP == 32
 
 template <int GROUP>
-__device__ __forceinline__ void group_ids(uint32_t &group, uint32_t &group_in_block, DevGroup<GROUP> &g) {
-    g.lane = threadIdx.x & 31;
-    g.lanes = 32;
+__device__ __forceinline__ void group_ids(uint32_t &group, uint32_t &group_in_block) {
     if (GROUP == 32) {
         group_in_block = threadIdx.x / 32;
         group = blockIdx.x * (blockDim.x / 32) + group_in_block;
-        g.tid = threadIdx.x & 31;
-        g.n = 32;
-        g.warp = 0;
-        g.nwarps = 1;
     } else {
         group_in_block = 0;
         group = blockIdx.x;
-        g.tid = threadIdx.x;
-        g.n = GROUP;
-        g.warp = threadIdx.x >> 5;
-        g.nwarps = GROUP / 32;
     }
+}
+
+// The Shot objects of a block: one per warp, in (static) shared memory -- see struct Shot.
+template <int GROUP>
+__device__ __forceinline__ Shot &block_shot() {
+    constexpr int WARPS = (GROUP == 32 ? WARP_MODE_BLOCK : GROUP) / 32;
+    __shared__ __align__(16) uint8_t shot_mem[WARPS * ((sizeof(Shot) + 15) / 16 * 16)];
+    return *(Shot *)(shot_mem + (threadIdx.x >> 5) * ((sizeof(Shot) + 15) / 16 * 16));
+}
+// bind_shot for this warp's copy: lane 0 writes, the warp waits.
+template <int GROUP>
+__device__ __forceinline__ void bind_warp_shot(Shot &s, const DecodeParams &p, const ScratchConfig &cfg, uint8_t *arena,
+                                               uint8_t *shared, const DevGroup<GROUP> &g) {
+    __syncwarp();
+    if (g.lane() == 0) bind_shot(s, p, cfg, arena, shared, g);
+    __syncwarp();
 }
 
 extern __shared__ __align__(16) uint8_t cb_smem[];
@@ -108,10 +116,10 @@ template <int GROUP>
 __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP) k_init_arena(DecodeParams p, uint32_t num_groups) {
     uint32_t group, gib;
     DevGroup<GROUP> g;
-    group_ids<GROUP>(group, gib, g);
+    group_ids<GROUP>(group, gib);
     if (group >= num_groups) return;
-    Shot s;
-    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, cb_smem, g);
+    Shot &s = block_shot<GROUP>();
+    bind_warp_shot<GROUP>(s, p, p.cfg, p.arena + (uint64_t)group * p.arena_stride, cb_smem, g);
     init_group_arena(s, g);
 }
 
@@ -169,23 +177,23 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
     uint32_t group, gib;
     DevGroup<GROUP> g;
     typedef typename std::conditional<PROF, PhaseTimer, NullTimer>::type Timer;
-    group_ids<GROUP>(group, gib, g);
+    group_ids<GROUP>(group, gib);
     if (group >= num_groups) return;
-    Shot s;
-    bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, cb_smem + (size_t)gib * smem_per_group, g);
+    Shot &s = block_shot<GROUP>();
+    bind_warp_shot<GROUP>(s, p, p.cfg, p.arena + (uint64_t)group * p.arena_stride, cb_smem + (size_t)gib * smem_per_group, g);
     init_group_shared(s, g);
     const uint32_t total = p.shot_list ? p.list_len : p.num_shots;
 #ifdef CB_TAIL_PROF
     // diagnostic build: slot 21 = first group's start (globaltimer ns), 20 = sum of group finish offsets, 22 = last finish
     unsigned long long tail_t0 = 0;
-    if (p.phase_cycles && g.tid == 0) {
+    if (p.phase_cycles && g.tid() == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         atomicCAS(&p.phase_cycles[21], 0ull, now);
     }
 #endif
     while (true) {
-        if (g.tid == 0) s.hdr->bcast = atomicAdd(p.work_counter, 1u);
+        if (g.tid() == 0) s.hdr->bcast = atomicAdd(p.work_counter, 1u);
         g.sync();
         uint32_t k = s.hdr->bcast;
         g.sync();
@@ -193,14 +201,14 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
         uint32_t shot = p.shot_list ? p.shot_list[k] : k;
         if (p.ready) {
             // streaming input: wait until the copy stream has delivered this shot's row
-            if (g.tid == 0) {
+            if (g.tid() == 0) {
                 while (*(const volatile uint32_t *)p.ready <= shot) __nanosleep(500);
                 __threadfence();
             }
             g.sync();
         }
         decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
-        if (p.event_total && g.tid == 0) {
+        if (p.event_total && g.tid() == 0) {
             const uint32_t ev = s.word_rank[s.nwords];  // detection events of the shot (set by ingest_shot, also on overflow)
             atomicAdd(p.event_total, (unsigned long long)ev);
             atomicMax(p.event_max, ev);
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
         // Out of scratch: again, in a spare arena with the next level's scratch, if one is free (decode_shot ended with a
         // barrier after thread 0 stored the status). Otherwise the host's retry launch takes the shot.
         if (p.spare_arena && p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) {
-            if (g.tid == 0) {
+            if (g.tid() == 0) {
                 uint32_t slot = NO_INDEX;
                 for (uint32_t c = 0; c < p.num_spares && slot == NO_INDEX; c++)
                     if (atomicCAS(&p.spare_claim[c], 0u, 1u) == 0u) slot = c;
@@ -219,21 +227,24 @@ __global__ void __launch_bounds__(GROUP == 32 ? WARP_MODE_BLOCK : GROUP, GROUP =
             g.sync();
             if (slot != NO_INDEX) {
                 uint8_t *const shared = cb_smem + (size_t)gib * smem_per_group;
-                bind_shot(s, p, p.spare_cfg, p.spare_arena + (uint64_t)slot * p.spare_stride, shared, g);
+                bind_warp_shot<GROUP>(s, p, p.spare_cfg, p.spare_arena + (uint64_t)slot * p.spare_stride, shared, g);
+                g.sync();
                 decode_shot<DevGroup<GROUP>, Timer>(s, p, shot, g);
-                if (g.tid == 0) {
+                if (g.tid() == 0) {
                     // still too small: tell the host that level 1 has been tried, so its retry starts at level 2
                     if (p.status_out[shot] == SHOT_SCRATCH_OVERFLOW) p.status_out[shot] = SHOT_SCRATCH_OVERFLOW_SPARE;
                     __threadfence();
                     atomicExch(&p.spare_claim[slot], 0u);
                     atomicAdd(p.spare_retries, 1u);
                 }
-                bind_shot(s, p, p.arena + (uint64_t)group * p.arena_stride, shared, g);
+                g.sync();  // thread 0 read the status through this binding
+                bind_warp_shot<GROUP>(s, p, p.cfg, p.arena + (uint64_t)group * p.arena_stride, shared, g);
+                g.sync();
             }
         }
     }
 #ifdef CB_TAIL_PROF
-    if (p.phase_cycles && g.tid == 0) {
+    if (p.phase_cycles && g.tid() == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         tail_t0 = *(volatile unsigned long long *)&p.phase_cycles[21];
@@ -445,9 +456,14 @@ void launch_decode(const DecodeParams &p, uint32_t groups, uint32_t smem_per_gro
         int dev = 0, sm_bytes = 0, resident = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        // occupancy with the largest carve-out (the attribute of an earlier launch would otherwise cap the answer)
+        cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_decode<GROUP>, (int)threads, smem);
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, k_decode<GROUP>);  // static shared memory: the warps' Shot objects
         int pct = -1;
-        if (sm_bytes > 0 && resident > 0) pct = (int)(((size_t)resident * (smem + 1024) * 100 + sm_bytes - 1) / sm_bytes);
+        if (sm_bytes > 0 && resident > 0)
+            pct = (int)(((size_t)resident * (smem + fa.sharedSizeBytes + 1024) * 100 + sm_bytes - 1) / sm_bytes);
         if (const char *env = getenv("CB200_CARVEOUT_PCT")) pct = atoi(env);  // experiments
         if (pct >= 0) cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
         cudaGetLastError();
@@ -465,6 +481,7 @@ int blocks_per_sm(size_t smem_per_group) {
     uint32_t per_block = GROUP == 32 ? WARP_MODE_BLOCK / 32 : 1;
     size_t smem = smem_per_group * per_block;
     int n = 0;
+    cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // see launch_decode
     if (cudaFuncSetAttribute(k_decode<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;

@@ -46,8 +46,10 @@
 // The sequential blossom code is latency bound and large; unrolled loops only make it miss the instruction cache.
 #ifdef __CUDACC__
 #define CB_LOOP _Pragma("unroll 1")
+#define CB_UNROLL _Pragma("unroll")
 #else
 #define CB_LOOP
+#define CB_UNROLL
 #endif
 
 namespace cb200 {
@@ -204,12 +206,12 @@ struct NullTimer {
 
 // A group of one thread with one-lane "warps": the host simulation, and the device's thread-per-shot mode.
 struct HostGroup {
-    int tid = 0;
-    int n = 1;
-    int lane = 0;
-    int lanes = 1;
-    int warp = 0;
-    int nwarps = 1;
+    CB_HD int tid() const { return 0; }
+    CB_HD int n() const { return 1; }
+    CB_HD int lane() const { return 0; }
+    CB_HD int lanes() const { return 1; }
+    CB_HD int warp() const { return 0; }
+    CB_HD int nwarps() const { return 1; }
     CB_HD void sync() const {}
     CB_HD void wsync() const {}
     CB_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
@@ -328,8 +330,12 @@ CB_HD uint64_t arena_bytes_per_group(const ScratchConfig &c, uint32_t num_nodes,
            event_bytes(c) + align16(c.dyn_bytes);
 }
 
-// Everything one group needs to decode one shot. Every thread of the group holds an identical copy (pointers are
-// computed with the same arithmetic), except the ball tables, which belong to the thread's warp.
+// Everything one group needs to decode one shot. One copy per WARP, in shared memory on the device (k_decode): the
+// copies of a group are identical (pointers are computed with the same arithmetic) except for the ball tables and the
+// small-allocation chunk, which belong to the warp. The object is passed by reference through the non-inlined stages; a
+// per-thread copy would live in local memory (~650 B per thread, 160 KB per 256-thread group, re-read on every field
+// access: measured as twice the global-load sectors of the whole kernel). After bind_shot the lanes only ever store
+// lane-uniform values into it (M, the chunk state by lane 0, the ball-table counters).
 struct Shot {
     TablesView T;
     ScratchConfig cfg;
@@ -417,8 +423,8 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, const ScratchConfig &cfg, u
     s.scan_tmp = (uint32_t *)q;
     q += align16(SCAN_TMP * 4);
     uint64_t gb = ball_table_bytes(cfg.ht_log2, cfg.found_cap);
-    bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp * gb, cfg.ht_log2, cfg.found_cap);
-    q += (uint64_t)g.nwarps * gb;
+    bind_ball_tables(s.gl_ball, q + (uint64_t)g.warp() * gb, cfg.ht_log2, cfg.found_cap);
+    q += (uint64_t)g.nwarps() * gb;
     uint64_t m = cfg.max_events;
     s.evdet = (uint32_t *)q; q += align16(m * 4);
     s.R = (int64_t *)q; q += align16(m * 8);
@@ -448,9 +454,9 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, const ScratchConfig &cfg, u
     s.words = (uint32_t *)sh; sh += align16(uint64_t{s.nwords} * 4);
     s.word_rank = (uint32_t *)sh; sh += align16((uint64_t{s.nwords} + 1) * 4);
     uint64_t sb = ball_table_bytes(cfg.sh_ht_log2, cfg.sh_found);
-    bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp * sb, cfg.sh_ht_log2, cfg.sh_found);
+    bind_ball_tables(s.sh_ball, sh + (uint64_t)g.warp() * sb, cfg.sh_ht_log2, cfg.sh_found);
     s.sh_tables = sh;
-    s.sh_tables_bytes = (uint64_t)g.nwarps * sb;
+    s.sh_tables_bytes = (uint64_t)g.nwarps() * sb;
     if (align16(cfg.sh_pool) > s.sh_tables_bytes) s.sh_tables_bytes = align16(cfg.sh_pool);
     // hot per-event arrays in shared memory (every pass of a matcher round re-reads them right after other threads of
     // the group wrote them, which always misses L1)
@@ -479,22 +485,22 @@ CB_HD void bind_shot(Shot &s, const DecodeParams &p, uint8_t *arena, uint8_t *sh
 // Called once per group before the first shot of a launch (shared memory does not survive launches).
 template <class G>
 CB_HD void init_group_shared(Shot &s, const G &g) {
-    for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
+    for (uint32_t k = g.lane(); k < s.sh_ball.H; k += g.lanes()) s.sh_ball.key[k] = HT_EMPTY;
     g.sync();
 }
 // Called once per arena layout.
 template <class G>
 CB_HD void init_group_arena(Shot &s, const G &g) {
-    for (uint32_t k = g.lane; k < s.gl_ball.H; k += g.lanes) s.gl_ball.key[k] = HT_EMPTY;
+    for (uint32_t k = g.lane(); k < s.gl_ball.H; k += g.lanes()) s.gl_ball.key[k] = HT_EMPTY;
     g.sync();
 }
 
-// Exclusive prefix sum of arr[0..n) in place, cooperatively; returns the total. Needs g.n <= SCAN_TMP.
+// Exclusive prefix sum of arr[0..n) in place, cooperatively; returns the total. Needs g.n() <= SCAN_TMP.
 template <class G>
 CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_t n) {
     // per-thread chunk sums -> inclusive scan inside the warp (shuffles) -> warp totals through scan_tmp
-    uint32_t chunk = (n + g.n - 1) / g.n;
-    uint32_t lo = (uint32_t)g.tid * chunk, hi = lo + chunk;
+    uint32_t chunk = (n + g.n() - 1) / g.n();
+    uint32_t lo = (uint32_t)g.tid() * chunk, hi = lo + chunk;
     if (lo > n) lo = n;
     if (hi > n) hi = n;
     uint32_t sum = 0;
@@ -502,17 +508,17 @@ CB_HDN uint32_t group_exclusive_scan(Shot &s, const G &g, uint32_t *arr, uint32_
     for (uint32_t k = lo; k < hi; k++) sum += arr[k];
     uint32_t incl = sum;
     CB_LOOP
-    for (int o = 1; o < g.lanes; o <<= 1) {
-        uint32_t t = g.shfl32(incl, g.lane >= o ? g.lane - o : g.lane);
-        if (g.lane >= o) incl += t;
+    for (int o = 1; o < g.lanes(); o <<= 1) {
+        uint32_t t = g.shfl32(incl, g.lane() >= o ? g.lane() - o : g.lane());
+        if (g.lane() >= o) incl += t;
     }
-    if (g.lane == g.lanes - 1) s.scan_tmp[g.warp] = incl;
+    if (g.lane() == g.lanes() - 1) s.scan_tmp[g.warp()] = incl;
     g.sync();
     uint32_t run = incl - sum, total = 0;
     CB_LOOP
-    for (int w = 0; w < g.nwarps; w++) {
+    for (int w = 0; w < g.nwarps(); w++) {
         uint32_t v = s.scan_tmp[w];
-        if (w < g.warp) run += v;
+        if (w < g.warp()) run += v;
         total += v;
     }
     CB_LOOP
@@ -543,14 +549,14 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
         if (head > full) head = full;
         const uint32_t body = (full - head) / 4;
         CB_LOOP
-        for (uint32_t w = g.tid; w < head; w += g.n) {
+        for (uint32_t w = g.tid(); w < head; w += g.n()) {
             const uint32_t v = row32[w] & mask32[w];
             s.words[w] = v;
             s.word_rank[w] = popc32(v);
         }
         const U4 *row128 = (const U4 *)(row32 + head);
         CB_LOOP
-        for (uint32_t k = g.tid; k < body; k += g.n) {
+        for (uint32_t k = g.tid(); k < body; k += g.n()) {
             const U4 r = row128[k];
             const uint32_t w = head + 4 * k;
             const uint32_t v0 = r.x & mask32[w], v1 = r.y & mask32[w + 1], v2 = r.z & mask32[w + 2], v3 = r.w & mask32[w + 3];
@@ -564,7 +570,7 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
             s.word_rank[w + 3] = popc32(v3);
         }
         CB_LOOP
-        for (uint32_t w = head + 4 * body + g.tid; w < s.nwords; w += g.n) {
+        for (uint32_t w = head + 4 * body + g.tid(); w < s.nwords; w += g.n()) {
             uint32_t v = 0;
             if (w < full) {
                 v = row32[w] & mask32[w];
@@ -580,7 +586,7 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
         }
     } else {
         CB_LOOP
-        for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
+        for (uint32_t w = g.tid(); w < s.nwords; w += g.n()) {
             uint32_t v = 0;
             CB_LOOP
             for (uint32_t b = 0; b < 4; b++) {
@@ -591,7 +597,7 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
             s.word_rank[w] = popc32(v);
         }
     }
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         s.hdr->status = 0;
         s.hdr->dyn_top = 0;
         s.hdr->weight = 0;
@@ -599,15 +605,15 @@ CB_HDN void ingest_shot(Shot &s, const uint8_t *row, const G &g) {
     }
     g.sync();
     uint32_t total = group_exclusive_scan(s, g, s.word_rank, s.nwords);
-    if (g.tid == 0) s.word_rank[s.nwords] = total;
+    if (g.tid() == 0) s.word_rank[s.nwords] = total;
     if (2 * total > s.cfg.max_events) {
-        if (g.tid == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.tid() == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         s.M = 0;
         g.sync();
         return;
     }
     CB_LOOP
-    for (uint32_t w = g.tid; w < s.nwords; w += g.n) {
+    for (uint32_t w = g.tid(); w < s.nwords; w += g.n()) {
         uint32_t run = s.word_rank[w];
         uint32_t v = s.words[w];
         CB_LOOP
@@ -642,7 +648,7 @@ CB_HD void ball_clear(BallTables &t, const G &g) {
     uint32_t *const key = t.key;
     const uint32_t *const used = t.used;
     const uint32_t n = t.nused;
-    for (uint32_t k = g.lane; k < n; k += g.lanes) key[used[k]] = HT_EMPTY;
+    for (uint32_t k = g.lane(); k < n; k += g.lanes()) key[used[k]] = HT_EMPTY;
     t.nused = t.nfront = 0;
     g.wsync();
 }
@@ -689,7 +695,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     uint32_t *const fslot = t.fslot;
     NbEntry *const found = t.found;
     const uint32_t H = t.H, hmask = t.H - 1, cap = t.cap, fcap = t.fcap;
-    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
     const uint32_t lane_lt = (1u << lane) - 1;
     const uint32_t ell_shift = s.T.ell_shift;
     const AdjEntry *const adj = ell_shift ? s.T.ell_adj : s.T.adj;
@@ -908,7 +914,7 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
     const uint32_t stride = s.T.near_stride;
     if (!stride) return false;
     const uint32_t src = s.event_node(i);
-    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
     const uint32_t lane_lt = (1u << lane) - 1;
     const uint32_t *const words = s.words;
     const uint32_t *const word_rank = s.word_rank;
@@ -1018,26 +1024,26 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
     }
     ball_clear(*t, g);
     if (r == BALL_OVERFLOW) {
-        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.lane() == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
     if (r == BALL_EXHAUSTED) {
         // Nothing more is reachable: this event cannot be paired (odd component of the Moebius graph).
-        if (g.lane == 0) s.fail(SHOT_NO_PERFECT_MATCHING);
+        if (g.lane() == 0) s.fail(SHOT_NO_PERFECT_MATCHING);
         return;
     }
     uint64_t off = 0;
-    if (g.lane == 0) {
+    if (g.lane() == 0) {
         uint8_t *dst = s.alloc_small(uint64_t{nfound} * sizeof(NbEntry) + 16);
         off = dst ? (uint64_t)(dst - s.dyn) + 1 : 0;
     }
     off = g.shfl64(off, 0);
     if (!off) return;
     NbEntry *dst = (NbEntry *)(s.dyn + (off - 1));
-    for (uint32_t k = g.lane; k < nfound; k += g.lanes) {
+    for (uint32_t k = g.lane(); k < nfound; k += g.lanes()) {
         dst[k] = t->found[k];
     }
-    if (g.lane == 0) {
+    if (g.lane() == 0) {
         s.regrown[i] = 1;
         s.nb_off[i] = (uint32_t)((off - 1) >> 4);
         s.nb_cnt[i] = nfound;
@@ -1052,7 +1058,7 @@ CB_HDN void explore_event(Shot &s, const G &g, uint32_t i, int64_t radius, uint3
 template <class G>
 CB_HDN void explore_first_near(Shot &s, const G &g) {
     const uint32_t M = s.M, stride = s.T.near_stride;
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         uint8_t *mem = stride ? s.alloc(uint64_t{M} * sizeof(NbEntry)) : nullptr;
         s.hdr->bcast = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
     }
@@ -1062,7 +1068,7 @@ CB_HDN void explore_first_near(Shot &s, const G &g) {
     if (!base) return;
     NbEntry *const lists = (NbEntry *)(s.dyn + ((uint64_t)(base - 1) << 4));
     const uint32_t *const words = s.words;
-    for (uint32_t i = (uint32_t)g.tid; i < M; i += (uint32_t)g.n) {
+    for (uint32_t i = (uint32_t)g.tid(); i < M; i += (uint32_t)g.n()) {
         const uint32_t src = s.event_node(i);
         for (uint32_t p = 0; p < stride; p += 4) {
             // rows are 256-byte aligned and p is a multiple of four: two independent 16-byte loads per step
@@ -1114,6 +1120,10 @@ CB_HDN void explore_first_near(Shot &s, const G &g) {
 #define CB_BLOSSOM_PAR_MIN 33
 #endif
 constexpr int BLOSSOM_PAR_MIN = CB_BLOSSOM_PAR_MIN;  // components with at least this many events use the warp helpers
+#ifndef CB_BLOSSOM_PAR_MIN_FIXED
+#define CB_BLOSSOM_PAR_MIN_FIXED 33  // > 32: the fixed 32-vertex layout never uses them
+#endif
+constexpr int BLOSSOM_PAR_MIN_FIXED = CB_BLOSSOM_PAR_MIN_FIXED;
 
 template <class G, int CAP = 0>
 struct Blossom {
@@ -1225,7 +1235,7 @@ struct Blossom {
         AW = (n + 32) / 32;
         wide = !CAP && n > (int)NARROW_COMPONENT;
         broken = false;
-        par = !CAP && lanes > 1 && n >= BLOSSOM_PAR_MIN;  // the fixed layouts are fastest on one lane
+        par = PAR_CLASS && lanes > 1 && n >= (CAP ? BLOSSOM_PAR_MIN_FIXED : BLOSSOM_PAR_MIN);
         n_x = n;
         if (CAP) return;
         uint8_t *p = mem + align16(sizeof(Blossom));
@@ -1248,7 +1258,10 @@ struct Blossom {
     }
     CB_HD int64_t &w(int u, int v) { return W()[u * ws() + v]; }
     CB_HD bool is_wide() const { return !CAP && wide; }
-    CB_HD bool is_par() const { return !CAP && par; }  // the fixed layouts always run on one lane
+    // The run-time layout always has the warp helpers; of the fixed layouts only the 32-vertex one (and only from
+    // BLOSSOM_PAR_MIN_FIXED events on): its O(n) loops are what a round waits for.
+    static constexpr bool PAR_CLASS = CAP == 0 || (CAP == 32 && BLOSSOM_PAR_MIN_FIXED <= 32);
+    CB_HD bool is_par() const { return PAR_CLASS && par; }
     CB_HD int geu(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2] : ge()[(a * nxs() + b) * 2]; }
     CB_HD int gev(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2 + 1] : ge()[(a * nxs() + b) * 2 + 1]; }
     CB_HD bool has(int a, int b) const { return geu(a, b) != 0; }
@@ -1400,7 +1413,7 @@ struct Blossom {
     // ---- warp dispatch: every lane runs the same helper; results are reduced with warp primitives ----
     CB_HDN uint64_t dispatch(const G &g, uint32_t op, uint32_t a0, uint32_t a1, uint32_t a2) {
         in_shared();
-        const int lane = g.lane, lanes = g.lanes;
+        const int lane = g.lane(), lanes = g.lanes();
         uint64_t r = 0;
         switch (op) {
             case OP_SET_SLACK:
@@ -1753,9 +1766,9 @@ struct Blossom {
     // parallel). W must be filled. Ends with the lanes synchronised.
     CB_HD void prepare(const G &g) {
         in_shared();
-        k_init(g.lane, g.lanes);
+        k_init(g.lane(), g.lanes());
         g.wsync();  // k_init clears lab[] with a different lane-to-vertex mapping
-        k_row_max_lab(g.lane, g.lanes);
+        k_row_max_lab(g.lane(), g.lanes());
         g.wsync();
     }
     // Master only, after prepare().
@@ -2037,7 +2050,7 @@ CB_HD uint64_t blossom_bytes(uint32_t n) {
 // across components are guarded by the dual check. Returns `big` (weights are big - distance).
 template <class G>
 CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n, const uint32_t *mem, int64_t *W, uint32_t ws) {
-    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
     CB_LOOP
     for (uint32_t k = lane; k < (n + 1) * ws; k += lanes) W[k] = 0;
     CB_LOOP
@@ -2073,7 +2086,7 @@ CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n,
 template <class G>
 CB_HDN void blossom_write_back(Shot &s, const G &g, uint32_t n, const uint32_t *mem, uint32_t pairs, int64_t big,
                                const uint16_t *match, const int64_t *lab) {
-    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
     if (pairs * 2 != n) {
         CB_LOOP
         for (uint32_t a = lane; a < n; a += lanes) {
@@ -2103,11 +2116,11 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     uint32_t n = s.cnt[r];
     uint32_t *mem = s.members + s.start[r];
     if (n > MAX_COMPONENT) {
-        if (g.lane == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
+        if (g.lane() == 0) s.fail(SHOT_COMPONENT_TOO_LARGE);
         return;
     }
     uint64_t off = 0;
-    if (g.lane == 0) {
+    if (g.lane() == 0) {
         uint8_t *memory = scratch ? scratch : s.alloc(BL::bytes_needed((int)n));
         off = memory ? (uint64_t)(uintptr_t)memory : 0;
     }
@@ -2115,13 +2128,13 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     if (!off) return;
     BL &bl = *BL::place((uint8_t *)(uintptr_t)off);
     bl.in_shared();
-    if (g.lane == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes);
+    if (g.lane() == 0) bl.bind((uint8_t *)(uintptr_t)off, (int)n, g.lanes());
     g.wsync();
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     const int64_t big = blossom_fill_weights(s, g, r, n, mem, bl.W(), (uint32_t)bl.ws());
     bl.prepare(g);
     uint32_t pairs = 0;
-    if (g.lane == 0) {
+    if (g.lane() == 0) {
         pairs = (uint32_t)bl.solve(g);
         bl.release_workers(g);
         if (s.prof) {
@@ -2138,7 +2151,7 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     g.wsync();
     pairs = g.shfl32(pairs, 0);
     if (pairs == NO_INDEX) {
-        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.lane() == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
     blossom_write_back(s, g, n, mem, pairs, big, bl.match(), bl.lab());
@@ -2171,7 +2184,7 @@ template <class G>
 CB_HDN void grow_some(Shot &s, const G &g, uint32_t limit) {
     while (true) {
         uint32_t k = NO_INDEX;
-        if (g.lane == 0) {
+        if (g.lane() == 0) {
             uint32_t cur = cb_load_volatile(&s.hdr->task_next);
             while (cur < limit) {
                 const uint32_t old = cb_atomic_cas(&s.hdr->task_next, cur, cur + 1);
@@ -2194,7 +2207,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
     const uint32_t M = s.M;
     s.chunk_left = 0;  // the dynamic region was reset for this shot
     CB_LOOP
-    for (uint32_t i = g.tid; i < M; i += g.n) {
+    for (uint32_t i = g.tid(); i < M; i += g.n()) {
         s.partner[i] = -1;
         s.solved[i] = 0;
         s.regrown[i] = 0;
@@ -2206,9 +2219,9 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         s.comp_dirty[i] = 0;
         s.cnt[i] = 0;
     }
-    if (g.tid == 0) s.hdr->ncomp = 0;
+    if (g.tid() == 0) s.hdr->ncomp = 0;
 #ifdef CB_TAIL_PROF
-    if (g.tid == 0) s.hdr->pad_hdr[0] = 0;  // largest component of the shot (diagnostic build)
+    if (g.tid() == 0) s.hdr->pad_hdr[0] = 0;  // largest component of the shot (diagnostic build)
 #endif
     g.sync();
 #ifdef CB_XPROF
@@ -2218,8 +2231,8 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
     CB_XLAP(s, g, xt, 12)
     // the few events whose row held no event: one warp each (the lanes look at 32 events at a time)
     CB_LOOP
-    for (uint32_t base = (uint32_t)g.warp * (uint32_t)g.lanes; base < M; base += (uint32_t)(g.nwarps * g.lanes)) {
-        const uint32_t i = base + (uint32_t)g.lane;
+    for (uint32_t base = (uint32_t)g.warp() * (uint32_t)g.lanes(); base < M; base += (uint32_t)(g.nwarps() * g.lanes())) {
+        const uint32_t i = base + (uint32_t)g.lane();
         uint32_t todo = g.ballot(i < M && s.nb_cnt[i] == 0);
         CB_LOOP
         while (todo) {
@@ -2236,7 +2249,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         pt.lap(round == 0 ? 1 : 4);
         if (s.hdr->status) return round;
         if (++round > MAX_ROUNDS) {
-            if (g.tid == 0) s.fail(SHOT_ROUND_LIMIT);
+            if (g.tid() == 0) s.fail(SHOT_ROUND_LIMIT);
             g.sync();
             return round;
         }
@@ -2245,19 +2258,19 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         // components used is reset here; everything else below touches all events in three passes only.
 #ifdef CB_XPROF2
         unsigned long long xt2 = cb_clock();
-#define CB_XLAP2(slot) if (s.prof && g.tid == 0) { unsigned long long now_ = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[slot], now_ - xt2); xt2 = now_; }
+#define CB_XLAP2(slot) if (s.prof && g.tid() == 0) { unsigned long long now_ = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[slot], now_ - xt2); xt2 = now_; }
 #else
 #define CB_XLAP2(slot)
 #endif
         const uint32_t prev_ncomp = s.hdr->ncomp;
         CB_LOOP
-        for (uint32_t c = g.tid; c < prev_ncomp; c += g.n) {
+        for (uint32_t c = g.tid(); c < prev_ncomp; c += g.n()) {
             const uint32_t r = s.comp_root[c];
             s.cnt[r] = 0;
             s.comp_dirty[r] = 0;
         }
         g.sync();
-        if (g.tid == 0) {
+        if (g.tid() == 0) {
             s.hdr->ncomp = 0;
             s.hdr->mem_top = 0;
             s.hdr->ngrow = 0;
@@ -2270,7 +2283,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         // A violated pair inside one solved component is either an old blossom-internal edge or a pair first seen after
         // the solve -- only a ball that grew since can show the latter, which marks it stale.
         CB_LOOP
-        for (uint32_t i = g.tid; i < M; i += g.n) {
+        for (uint32_t i = g.tid(); i < M; i += g.n()) {
             const bool si = s.solved[i] != 0;
             const NbEntry *l = nb_list(s, i);
             CB_LOOP
@@ -2285,7 +2298,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         g.sync();
         CB_XLAP2(12)
         CB_LOOP
-        for (uint32_t i = g.tid; i < M; i += g.n) {
+        for (uint32_t i = g.tid(); i < M; i += g.n()) {
             uint32_t r = uf_find(s.uf, i);
             s.root[i] = r;
             s.uf[i] = r;  // path compression (concurrent finds still see an ancestor)
@@ -2297,7 +2310,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         g.sync();
         CB_XLAP2(13)
         CB_LOOP
-        for (uint32_t i = g.tid; i < M; i += g.n)
+        for (uint32_t i = g.tid(); i < M; i += g.n())
             if (s.comp_dirty[s.root[i]]) {
                 cb_atomic_add(&s.cnt[s.root[i]], 1);
                 act[cb_atomic_add(&s.hdr->nhuge, 1)] = i;
@@ -2306,7 +2319,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         CB_XLAP2(14)
         const uint32_t nact = s.hdr->nhuge;
         CB_LOOP
-        for (uint32_t k = g.tid; k < nact; k += g.n) {
+        for (uint32_t k = g.tid(); k < nact; k += g.n()) {
             const uint32_t i = act[k];
             if (s.root[i] == i) {
                 uint32_t slot = cb_atomic_add(&s.hdr->ncomp, 1);
@@ -2320,7 +2333,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         }
         g.sync();
         CB_LOOP
-        for (uint32_t k = g.tid; k < nact; k += g.n) {
+        for (uint32_t k = g.tid(); k < nact; k += g.n()) {
             const uint32_t i = act[k];
             const uint32_t r = s.root[i];
             uint32_t p = cb_atomic_add(&s.fillp[r], 1);
@@ -2333,7 +2346,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
         pt.lap(2);
         // small components: one thread each; the rest is queued for the blossom
         CB_LOOP
-        for (uint32_t c = g.tid; c < ncomp; c += g.n)
+        for (uint32_t c = g.tid(); c < ncomp; c += g.n())
             if (!solve_component_small(s, c)) s.blist[cb_atomic_add(&s.hdr->nbig, 1)] = c;
         g.sync();
         pt.lap(8);
@@ -2349,7 +2362,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             // order: (size descending, root ascending), by counting predecessors -- one thread per component.
             // s.path_off (unused until the path phase) receives the ordered list, s.fillp the sizes.
             CB_LOOP
-            for (uint32_t k = (uint32_t)g.tid; k < nbig; k += (uint32_t)g.n) {
+            for (uint32_t k = (uint32_t)g.tid(); k < nbig; k += (uint32_t)g.n()) {
                 const uint32_t v = s.blist[k], vr = s.comp_root[v], vn = s.cnt[vr];
                 uint32_t rank = 0;
                 CB_LOOP
@@ -2361,7 +2374,7 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
                 s.fillp[rank] = vn;
             }
             g.sync();
-            if (g.tid == 0) {
+            if (g.tid() == 0) {
                 const uint64_t pool = s.sh_tables_bytes;
                 uint32_t wave = 0;
                 uint64_t top = 0;
@@ -2393,8 +2406,8 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
                 const uint32_t k0 = s.scan_tmp[wave], k1 = s.scan_tmp[wave + 1];
                 // largest first, dealt out in serpentine order (warp 0 gets the 1st and the 16th, warp 7 the 8th and 9th)
                 CB_LOOP
-                for (uint32_t base = k0, pass = 0; base < k1; base += g.nwarps, pass++) {
-                    const uint32_t k = base + ((pass & 1) ? (uint32_t)(g.nwarps - 1 - g.warp) : (uint32_t)g.warp);
+                for (uint32_t base = k0, pass = 0; base < k1; base += g.nwarps(), pass++) {
+                    const uint32_t k = base + ((pass & 1) ? (uint32_t)(g.nwarps() - 1 - g.warp()) : (uint32_t)g.warp());
                     if (k >= k1) continue;
                     const uint32_t off16 = s.fillp[k];
                     solve_component_blossom(s, g, s.path_off[k], off16 == 0xFFFFu ? nullptr : s.sh_tables + ((uint64_t)off16 << 4));
@@ -2407,11 +2420,11 @@ CB_HDN uint32_t match_shot(Shot &s, const G &g, PT &pt) {
             }
             pt.lap(9);
 #ifdef CB_WAVE_PROF
-            if (s.prof && g.tid == 0) cb_atomic_add64((uint64_t *)&s.prof[12 + (round < 4 ? round - 1 : 3)], pt.t[9] - wave_prof_before);
+            if (s.prof && g.tid() == 0) cb_atomic_add64((uint64_t *)&s.prof[12 + (round < 4 ? round - 1 : 3)], pt.t[9] - wave_prof_before);
 #endif
             if (s.sh_ball.H)
                 CB_LOOP
-                for (uint32_t k = g.lane; k < s.sh_ball.H; k += g.lanes) s.sh_ball.key[k] = HT_EMPTY;
+                for (uint32_t k = g.lane(); k < s.sh_ball.H; k += g.lanes()) s.sh_ball.key[k] = HT_EMPTY;
         }
         g.sync();
         pt.lap(10);
@@ -2463,7 +2476,7 @@ template <class G>
 CB_HDN bool extract_path_near(Shot &s, const G &g, uint32_t i, uint32_t src, uint32_t dst, int64_t d_total) {
     const uint32_t stride = s.T.near_stride;
     if (!stride) return false;
-    const uint32_t lane = (uint32_t)g.lane, lanes = (uint32_t)g.lanes;
+    const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
     uint32_t at = NO_INDEX;
     for (uint32_t pos = 0; pos < stride; pos += lanes) {
         const NearEntry e = *near_at(s.T, src, pos + lane);
@@ -2492,8 +2505,8 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
         const RowRange row = row_of(s.T, src);
         const AdjEntry *adj = adj_of(s.T);
         bool direct = false;
-        for (uint32_t base = row.e0; base < row.e1 && !direct; base += g.lanes) {
-            uint32_t e = base + g.lane;
+        for (uint32_t base = row.e0; base < row.e1 && !direct; base += g.lanes()) {
+            uint32_t e = base + g.lane();
             bool hit = false;
             if (e < row.e1) {
                 AdjEntry a = adj[e];
@@ -2503,7 +2516,7 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
         }
         if (direct) {
             uint64_t off = 0;
-            if (g.lane == 0) {
+            if (g.lane() == 0) {
                 uint8_t *mem = s.alloc_small(8);
                 off = mem ? (uint64_t)(mem - s.dyn) + 1 : 0;
                 if (mem) {
@@ -2534,7 +2547,7 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
         uint32_t cur = dst;
         int64_t dc = d_total;
         uint32_t pos = len;
-        if (pass == 1 && g.lane == 0) out[pos - 1] = cur;
+        if (pass == 1 && g.lane() == 0) out[pos - 1] = cur;
         pos--;
         uint32_t steps = 0;
         while (cur != src) {
@@ -2542,8 +2555,8 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
             const AdjEntry *adj = adj_of(s.T);
             uint32_t best = NO_INDEX;
             int64_t bd = 0;
-            for (uint32_t base = row.e0; base < row.e1 && best == NO_INDEX; base += g.lanes) {
-                uint32_t e = base + g.lane;
+            for (uint32_t base = row.e0; base < row.e1 && best == NO_INDEX; base += g.lanes()) {
+                uint32_t e = base + g.lane();
                 bool hit = false;
                 int64_t dv = -1;
                 uint32_t nbr = 0;
@@ -2568,13 +2581,13 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
             }
             cur = best;
             dc = bd;
-            if (pass == 1 && g.lane == 0) out[pos - 1] = cur;
+            if (pass == 1 && g.lane() == 0) out[pos - 1] = cur;
             pos--;
             if (pass == 0) len++;
         }
         if (pass == 0 && ok) {
             uint64_t off = 0;
-            if (g.lane == 0) {
+            if (g.lane() == 0) {
                 uint8_t *mem = s.alloc_small(uint64_t{len} * 4);
                 off = mem ? (uint64_t)(mem - s.dyn) + 1 : 0;
             }
@@ -2588,10 +2601,10 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
     }
     ball_clear(*t, g);
     if (!ok) {
-        if (g.lane == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
+        if (g.lane() == 0) s.fail(SHOT_SCRATCH_OVERFLOW);
         return;
     }
-    if (g.lane == 0) {
+    if (g.lane() == 0) {
         s.path_off[i] = (uint32_t)(((uint8_t *)out - s.dyn) >> 4);
         s.path_len[i] = len;
     }
@@ -2600,14 +2613,14 @@ CB_HDN void extract_path(Shot &s, const G &g, uint32_t i, uint32_t j, int64_t d_
 
 template <class G>
 CB_HDN void paths_shot(Shot &s, const G &g) {
-    for (uint32_t i = g.tid; i < s.M; i += g.n) s.path_len[i] = 0;
+    for (uint32_t i = g.tid(); i < s.M; i += g.n()) s.path_len[i] = 0;
     g.sync();
 #ifdef CB_XPROF
     unsigned long long xt = cb_clock();
 #endif
     // Pairs whose partner sits in the near-table row of the smaller event: one thread each.
     uint64_t wsum = 0;
-    for (uint32_t i = (uint32_t)g.tid; i < s.M; i += (uint32_t)g.n) {
+    for (uint32_t i = (uint32_t)g.tid(); i < s.M; i += (uint32_t)g.n()) {
         const int32_t j = s.partner[i];
         if (j <= (int32_t)i) continue;
         const NbEntry *l = nb_list(s, i);
@@ -2654,8 +2667,8 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
     CB_XLAP(s, g, xt, 14)
     // The rest (seen only from the partner's side, or found by a search): one warp each.
     wsum = 0;
-    for (uint32_t base = (uint32_t)g.warp * (uint32_t)g.lanes; base < s.M; base += (uint32_t)(g.nwarps * g.lanes)) {
-        const uint32_t mine = base + (uint32_t)g.lane;  // the lanes look at 32 events at a time
+    for (uint32_t base = (uint32_t)g.warp() * (uint32_t)g.lanes(); base < s.M; base += (uint32_t)(g.nwarps() * g.lanes())) {
+        const uint32_t mine = base + (uint32_t)g.lane();  // the lanes look at 32 events at a time
         uint32_t todo = g.ballot(mine < s.M && s.partner[mine] > (int32_t)mine && s.path_len[mine] == 0);
         while (todo) {
             const uint32_t i = base + ctz32(todo);
@@ -2666,7 +2679,7 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
             extract_path(s, g, i, j, d);
         }
     }
-    if (wsum && g.lane == 0) cb_atomic_add64(&s.hdr->weight, wsum);
+    if (wsum && g.lane() == 0) cb_atomic_add64(&s.hdr->weight, wsum);
     g.sync();
     CB_XLAP(s, g, xt, 15)
 }
@@ -2682,10 +2695,6 @@ CB_HDN void paths_shot(Shot &s, const G &g) {
 // node, which makes each cycle identical to the reference's and the XOR of the cycle results order independent.
 // Half-edge q = 2 * edge + side; edges are numbered in emission order, matched edges first, then doubling edges.
 // ---------------------------------------------------------------------------------------------------------------
-struct OptMask {
-    uint64_t v[4];
-    uint32_t has;  // bit c set <=> state c holds a value
-};
 
 CB_HD uint32_t find_half_edge(const TablesView &T, uint32_t from, uint32_t to) {
     for (uint32_t e = T.row_ptr[from]; e < T.row_ptr[from + 1]; e++)
@@ -2698,9 +2707,10 @@ CB_HD uint32_t find_half_edge(const TablesView &T, uint32_t from, uint32_t to) {
 // `mmm.find`, precomputed per edge by lift_shot). Nothing the loop loads depends on the running charge state except the
 // observable mask itself, so the next step's node, drag index and valid bits are fetched one step ahead.
 CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, const uint32_t *cyc_di, uint32_t len, uint32_t start, uint64_t *out) {
-    OptMask cur;
-    cur.has = 1u << start;
-    cur.v[0] = cur.v[1] = cur.v[2] = cur.v[3] = 0;
+    // The four optional charge states live in named scalars (`has` bit c set <=> state c holds a value): an array
+    // indexed by the run-time colour would sit in local memory, and this loop was a quarter of the kernel's local traffic.
+    uint32_t has = 1u << start;
+    uint64_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
     uint32_t cur_node = cycle[len - 1];
     uint32_t cur_loc = cur_node >> 1;
     uint32_t pf_node = cycle[0], pf_di = cyc_di[0];
@@ -2714,40 +2724,53 @@ CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, const uint32_
         }
         bool has_event = s.node_is_event(cur_node);
         uint32_t evi = has_event ? (s.node_event_index(cur_node) >> 1) : 0;
-        OptMask after;
-        after.has = 0;
-        after.v[0] = after.v[1] = after.v[2] = after.v[3] = 0;
+        uint32_t ahas = 0;
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        auto get = [&](uint32_t i) -> uint64_t { return i == 0 ? v0 : (i == 1 ? v1 : (i == 2 ? v2 : v3)); };
+        auto set = [&](uint32_t i, uint64_t x) {
+            a0 = i == 0 ? x : a0;
+            a1 = i == 1 ? x : a1;
+            a2 = i == 2 ? x : a2;
+            a3 = i == 3 ? x : a3;
+            ahas |= 1u << i;
+        };
         if (next_loc == cur_loc && has_event && !s.used_flag[evi]) {
             s.used_flag[evi] = 1;
             uint8_t info = s.T.det_info[cur_loc];
             uint32_t dc = info & DET_COLOR_MASK;
-            if (cur.has & 1u) { after.v[dc] = cur.v[0]; after.has |= 1u << dc; }
-            if (cur.has & (1u << dc)) { after.v[0] = cur.v[dc]; after.has |= 1u; }
-            if (dc == 0) {
-                // unreachable for valid tables (events never sit on NEUTRAL detectors); mirror optional semantics:
-                // after[dc] = cur[NEUTRAL]; after[NEUTRAL] = cur[dc] with dc == NEUTRAL keeps cur[NEUTRAL].
-            }
+            // after[dc] = cur[NEUTRAL]; after[NEUTRAL] = cur[dc] (dc == NEUTRAL is unreachable for valid tables: events
+            // never sit on NEUTRAL detectors; the optional semantics then keep cur[NEUTRAL])
+            if (has & 1u) set(dc, v0);
+            if (has & (1u << dc)) set(0, get(dc));
             if (info & DET_REP_WEIGHT3) {
                 uint32_t c1 = dc % 3 + 1, c2 = c1 % 3 + 1;
                 uint64_t f = s.T.rep_obs[cur_loc];
-                if (cur.has & (1u << c1)) { after.v[c2] = cur.v[c1] ^ f; after.has |= 1u << c2; }
-                if (cur.has & (1u << c2)) { after.v[c1] = cur.v[c2] ^ f; after.has |= 1u << c1; }
+                if (has & (1u << c1)) set(c2, get(c1) ^ f);
+                if (has & (1u << c2)) set(c1, get(c2) ^ f);
             }
         } else if (di != NO_INDEX) {
             const bool forward = cur_loc <= next_loc;  // walking the stored (min, max) orientation
             const DragEntry &de = s.T.drag[di];
+            CB_UNROLL
             for (uint32_t cc = 0; cc < 4; cc++) {
-                if (!(cur.has & (1u << cc))) continue;
+                if (!(has & (1u << cc))) continue;
+                const uint64_t vc = cc == 0 ? v0 : (cc == 1 ? v1 : (cc == 2 ? v2 : v3));
+                CB_UNROLL
                 for (uint32_t nc = 0; nc < 4; nc++) {
                     uint32_t bit = forward ? 4 * cc + nc : 4 * nc + cc;
                     if (valid & (1u << bit)) {
-                        after.v[nc] = cur.v[cc] ^ de.obs[bit];
-                        after.has |= 1u << nc;
+                        const uint64_t x = vc ^ de.obs[bit];
+                        if (nc == 0) a0 = x;
+                        else if (nc == 1) a1 = x;
+                        else if (nc == 2) a2 = x;
+                        else a3 = x;
+                        ahas |= 1u << nc;
                     }
                 }
             }
         }
-        cur = after;
+        has = ahas;
+        v0 = a0; v1 = a1; v2 = a2; v3 = a3;
         cur_node = next_node;
         cur_loc = next_loc;
     }
@@ -2756,8 +2779,8 @@ CB_HDN bool discharge_single_start(Shot &s, const uint32_t *cycle, const uint32_
         uint32_t nd = cycle[k];
         if (s.node_is_event(nd)) s.used_flag[s.node_event_index(nd) >> 1] = 0;
     }
-    if (cur.has & (1u << start)) {
-        *out = cur.v[start];
+    if (has & (1u << start)) {
+        *out = start == 0 ? v0 : (start == 1 ? v1 : (start == 2 ? v2 : v3));
         return true;
     }
     return false;
@@ -2969,7 +2992,7 @@ template <class G>
 CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     const uint32_t M = s.M;
     // a. junction test over the interior nodes of the paths (most paths are a single edge and have none)
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         s.hdr->scan_total = 0;   // number of interior nodes
         s.hdr->lift_ncomp = 0;   // junction flag
         s.hdr->lift_cyc_top = 0; // cycle buffer bump pointer
@@ -2979,7 +3002,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     {
         uint32_t interior = 0, edges = 0;
         CB_LOOP
-        for (uint32_t i = g.tid; i < M; i += g.n) {
+        for (uint32_t i = g.tid(); i < M; i += g.n()) {
             const uint32_t len = s.path_len[i];
             if (len >= 2) edges += len - 1;
             if (len > 2) interior += len - 2;
@@ -2997,7 +3020,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
         while (HK < 2 * ninterior) HK <<= 1;
     }
     g.sync();
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         uint8_t *mem = s.alloc((uint64_t{2} * E + 8 + HK) * 4);
         s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
     }
@@ -3010,10 +3033,10 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     uint32_t *hkey = cyc_di + E + 4;
     if (HK) {
         CB_LOOP
-        for (uint32_t k = g.tid; k < HK; k += g.n) hkey[k] = HT_EMPTY;
+        for (uint32_t k = g.tid(); k < HK; k += g.n()) hkey[k] = HT_EMPTY;
         g.sync();
         CB_LOOP
-        for (uint32_t i = g.tid; i < M; i += g.n) {
+        for (uint32_t i = g.tid(); i < M; i += g.n()) {
             const uint32_t len = s.path_len[i];
             if (len <= 2) continue;
             const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
@@ -3039,7 +3062,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     }
     // b. one thread per detection event: the component's smallest event walks, stores and discharges its cycle
     CB_LOOP
-    for (uint32_t i = 2 * (uint32_t)g.tid; i < M; i += 2 * (uint32_t)g.n) {
+    for (uint32_t i = 2 * (uint32_t)g.tid(); i < M; i += 2 * (uint32_t)g.n()) {
         const uint32_t len = plain_cycle_length(s, i, E);
         if (!len) {
             // not the minimum of its component -- or a broken structure, which the minimum's own walk reports
@@ -3065,7 +3088,7 @@ CB_HDN bool lift_shot_plain(Shot &s, const G &g) {
     }
     g.sync();
     // every half-edge belongs to exactly one cycle: the cycles together hold E nodes, or some walk did not close
-    if (g.tid == 0 && !s.hdr->status && s.hdr->lift_cyc_top != E) s.fail(SHOT_EULER_FAILED);
+    if (g.tid() == 0 && !s.hdr->status && s.hdr->lift_cyc_top != E) s.fail(SHOT_EULER_FAILED);
     g.sync();
     return true;
 }
@@ -3074,13 +3097,13 @@ template <class G>
 CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dump_cap, uint64_t *edge_dump_len) {
 #ifdef CB_LIFT_PROF
     unsigned long long lp_t = cb_clock();
-#define CB_LIFT_LAP(k) if (s.prof && g.tid == 0) { unsigned long long now = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[k], now - lp_t); lp_t = now; }
+#define CB_LIFT_LAP(k) if (s.prof && g.tid() == 0) { unsigned long long now = cb_clock(); cb_atomic_add64((uint64_t *)&s.prof[k], now - lp_t); lp_t = now; }
 #else
 #define CB_LIFT_LAP(k)
 #endif
     const uint32_t M = s.M;
     // edge numbering: exclusive scan of (path_len - 1) over events -> s.start
-    for (uint32_t i = g.tid; i < M; i += g.n) s.start[i] = s.path_len[i] ? s.path_len[i] - 1 : 0;
+    for (uint32_t i = g.tid(); i < M; i += g.n()) s.start[i] = s.path_len[i] ? s.path_len[i] - 1 : 0;
     g.sync();
     LiftArrays L;
     L.EM = group_exclusive_scan(s, g, s.start, M);
@@ -3091,7 +3114,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     L.M = M;
     L.HK = 16;
     while (L.HK < 2 * (L.EM > M / 2 ? L.EM - M / 2 : 0)) L.HK <<= 1;
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         uint8_t *mem = s.alloc((uint64_t{HE} * 11 + 1) * 4 + 16 * 20 + (uint64_t{3} * E + 8) * 8 + uint64_t{E} * 4 + uint64_t{HE} * 2 +
                                (uint64_t{M} + 2 * uint64_t{L.HK}) * 4);
         s.hdr->scan_total = mem ? (uint32_t)((mem - s.dyn) >> 4) + 1 : 0;
@@ -3116,10 +3139,10 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
         L.node_min = (uint32_t *)p; p += align16((uint64_t{M} + L.HK) * 4);
         L.hkey = (uint32_t *)p;
     }
-    for (uint32_t k = g.tid; k < M + L.HK; k += g.n) L.node_min[k] = NO_INDEX;
-    for (uint32_t k = g.tid; k < L.HK; k += g.n) L.hkey[k] = HT_EMPTY;
+    for (uint32_t k = g.tid(); k < M + L.HK; k += g.n()) L.node_min[k] = NO_INDEX;
+    for (uint32_t k = g.tid(); k < L.HK; k += g.n()) L.hkey[k] = HT_EMPTY;
     // a. endpoints of every half-edge
-    for (uint32_t i = g.tid; i < M; i += g.n) {
+    for (uint32_t i = g.tid(); i < M; i += g.n()) {
         uint32_t len = s.path_len[i];
         if (len) {
             const uint32_t *p = (const uint32_t *)(s.dyn + ((uint64_t)s.path_off[i] << 4));
@@ -3141,7 +3164,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     }
     g.sync();
     // b. list id of a node = its smallest half-edge
-    for (uint32_t q = g.tid; q < HE; q += g.n) {
+    for (uint32_t q = g.tid(); q < HE; q += g.n()) {
         const uint32_t id = lift_node_id(s, L, L.own[q], true);
         L.slot[q] = id;  // compact node id for now, the list id after the next pass
         cb_atomic_min(&L.node_min[id], q);
@@ -3156,13 +3179,13 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     }
     g.sync();
     // c. degrees and connectivity
-    for (uint32_t q = g.tid; q < HE; q += g.n) {
+    for (uint32_t q = g.tid(); q < HE; q += g.n()) {
         uint32_t sl = L.node_min[L.slot[q]];
         L.slot[q] = sl;
         cb_atomic_add(&L.lstart[sl], 1);
     }
     g.sync();
-    for (uint32_t e = g.tid; e < E; e += g.n) {
+    for (uint32_t e = g.tid(); e < E; e += g.n()) {
         uf_union(L.uf, L.slot[2 * e], L.slot[2 * e + 1]);
         // the drag-table entry the discharge will need for this edge (decoder.cc:104-127: mmm.find of the detector pair)
         const uint32_t a = L.own[2 * e], b = L.own[2 * e + 1];
@@ -3179,17 +3202,17 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     CB_LIFT_LAP(12)
     // d. list offsets
     uint32_t total = group_exclusive_scan(s, g, L.lstart, HE);
-    if (g.tid == 0) L.lstart[HE] = total;
+    if (g.tid() == 0) L.lstart[HE] = total;
     g.sync();
     // e. fill
-    for (uint32_t q = g.tid; q < HE; q += g.n) {
+    for (uint32_t q = g.tid(); q < HE; q += g.n()) {
         uint32_t sl = L.slot[q];
         uint32_t p = L.lstart[sl] + cb_atomic_add(&L.fillc[sl], 1);
         L.lst[p] = q;
     }
     g.sync();
     // f. restore edge-list order inside every list; component bookkeeping
-    for (uint32_t q = g.tid; q < HE; q += g.n) {
+    for (uint32_t q = g.tid(); q < HE; q += g.n()) {
         if (L.slot[q] == q) {
             uint32_t a0 = L.lstart[q], a1 = L.lstart[q + 1];
             for (uint32_t a = a0 + 1; a < a1; a++) {
@@ -3216,7 +3239,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     }
     g.sync();
     // g. component list and cycle buffers
-    for (uint32_t q = g.tid; q < HE; q += g.n)
+    for (uint32_t q = g.tid(); q < HE; q += g.n())
         if (L.slot[q] == q && uf_find(L.uf, q) == q) {
             uint32_t k = cb_atomic_add(&s.hdr->lift_ncomp, 1);
             L.comps[k] = q;
@@ -3225,7 +3248,7 @@ CB_HDN void lift_shot(Shot &s, const G &g, int64_t *edge_dump, uint64_t edge_dum
     const uint32_t ncomp = s.hdr->lift_ncomp;
     CB_LIFT_LAP(13)
     // h. one thread per component
-    for (uint32_t c = g.tid; c < ncomp; c += g.n) {
+    for (uint32_t c = g.tid(); c < ncomp; c += g.n()) {
         uint32_t root = L.comps[c];
         uint32_t off = cb_atomic_add(&s.hdr->lift_cyc_top, L.cedges[root] + 2);
         if (L.cmin[root] == NO_INDEX) {
@@ -3259,11 +3282,11 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
         // the plain-cycle lift covers shots without junctions; the edge dump (a debugging hook) needs the general one
         const bool plain = !p.edge_dump && !p.edge_dump_len && !(s.cfg.pad & 1u) && lift_shot_plain(s, g);
         if (!plain) lift_shot(s, g, p.edge_dump, p.edge_dump_cap, p.edge_dump_len);
-    } else if (g.tid == 0 && p.edge_dump_len) {
+    } else if (g.tid() == 0 && p.edge_dump_len) {
         *p.edge_dump_len = 0;
     }
     g.sync();
-    if (g.tid == 0) {
+    if (g.tid() == 0) {
         pt.lap(6);
         if (p.phase_cycles) {
             pt.t[3] = pt.t[8] + pt.t[9] + pt.t[10];
