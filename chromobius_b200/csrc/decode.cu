@@ -639,8 +639,18 @@ int decode_impl(cb200_decoder *d, const uint8_t *dets, uint64_t num_shots, uint6
     // already works on the chunks that have arrived. The arena is sized from the first chunk (plus head room; a shot
     // beyond it takes the scratch-overflow retry path), so the kernel can start after one chunk instead of after the
     // whole copy and a count pass over all of it.
+    // Not when launches are serialised with their stream's other work (CUDA_LAUNCH_BLOCKING=1, a profiler or sanitizer
+    // injected into the process): the kernel would wait for chunks whose copies cannot start before it ends.
+    auto launches_serialised = [] {
+        const char *b = getenv("CUDA_LAUNCH_BLOCKING");
+        if (b && b[0] == '1') return true;
+        for (const char *name : {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE",
+                                 "NV_SANITIZER_INJECTION_TRANSPORT_TYPE"})
+            if (getenv(name)) return true;
+        return false;
+    };
     uint64_t chunk = 0;
-    if (!dev_io && nb && !getenv("CB200_NO_PIPELINE")) {
+    if (!dev_io && nb && !getenv("CB200_NO_PIPELINE") && !launches_serialised()) {
         chunk = std::max<uint64_t>(8192, ((uint64_t)96 << 20) / nb);
         if (const char *env = getenv("CB200_PIPELINE_CHUNK")) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
         if ((uint64_t)n < 3 * chunk) chunk = 0;

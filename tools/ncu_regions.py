@@ -35,7 +35,7 @@ def line_of(pattern):
             return k + 1
     raise SystemExit('pattern not found: ' + pattern)
 marks = [('ingest / explore / ball', r'void ingest_shot\('), ('blossom struct', r'^struct Blossom \{'), ('union-find / solve_component_* / fill / writeback', r'uint32_t uf_find\('),
-         ('grow_some', r'void grow_some\('), ('match_shot (rounds, waves)', r'uint32_t match_shot\('), ('paths', r'bool near_path_emit\('), ('lift + discharge', r'^struct OptMask')]
+         ('grow_some', r'void grow_some\('), ('match_shot (rounds, waves)', r'uint32_t match_shot\('), ('paths', r'bool near_path_emit\('), ('lift + discharge', r'^CB_HD uint32_t find_half_edge')]
 bounds = [(name, line_of(pat)) for name, pat in marks] + [('end', len(src_lines) + 1)]
 ranges = {'%s (%d-%d)' % (bounds[k][0], bounds[k][1], bounds[k + 1][1]): (bounds[k][1], bounds[k + 1][1]) for k in range(len(marks))}
 tot=sum(c['samples'] for c in per.values())
