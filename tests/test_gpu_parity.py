@@ -1,10 +1,13 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded shots."""
+import os
+
 import numpy as np
 import pytest
 
 from dem_util import read_dem, NumpyDemSampler
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [
     # (dem, shots, seed)
@@ -131,6 +134,31 @@ def test_streaming_host_input_gives_the_same_answers(libs, monkeypatch, name, sh
     wide = np.zeros((shots, dets.shape[1] + 3), np.uint8)
     wide[:, :dets.shape[1]] = dets
     assert (dec2.predict_obs_flips_from_dets_bit_packed(wide[:, :dets.shape[1]]) == pred0).all()
+
+
+def test_streaming_input_is_off_when_launches_are_serialised():
+    """CUDA_LAUNCH_BLOCKING=1 (or an injected profiler) lets a launch finish before the next copy starts: a persistent
+    kernel waiting for streamed chunks would never end. The library must fall back to copy-then-decode."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import chromobius_b200 as cb\n"
+        "from dem_util import read_dem, NumpyDemSampler\n"
+        "text = read_dem('midout_color_code_d9_r36_p1000')\n"
+        "dets, _ = NumpyDemSampler(text).sample(6000, 3)\n"
+        "os.environ['CB200_PIPELINE_CHUNK'] = '1000'\n"
+        "a = cb._compile_text(text, device=0).decode_with_integer_weights(dets)\n"
+        "os.environ['CUDA_LAUNCH_BLOCKING'] = '1'\n"
+        "b = cb._compile_text(text, device=0).decode_with_integer_weights(dets)\n"
+        "assert (a[0] == b[0]).all() and (a[1] == b[1]).all()\n"
+        "print('ok')\n") % (ROOT, os.path.join(ROOT, 'tests'))
+    env = dict(os.environ)
+    env['CUDA_LAUNCH_BLOCKING'] = '1'
+    env['PYTHONPATH'] = os.path.join(ROOT, 'tools') + os.pathsep + env.get('PYTHONPATH', '')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
 
 
 def test_plain_cycle_lift_equals_general_lift(libs, monkeypatch):
