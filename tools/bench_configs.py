@@ -75,11 +75,15 @@ def main():
                 first = (d_dets[:max(n_check, 1)].cpu().numpy().copy(), pred64[:n_check].cpu().numpy().astype(np.uint64),
                          d_w[:n_check].cpu().numpy().copy())
         gpu_rate = calls * per_call / (ms_dev * 1e-3)
-        # host API (pinned host input, host output), one call
+        # host API (pinned host input, host output): the first full-size call (it allocates the staging buffers and
+        # sizes the arena) and the one after it
         h = torch.empty((per_call, nb), dtype=torch.uint8).pin_memory()
         h.copy_(d_dets)
         hn = h.numpy()
         dec.predict_obs_flips_from_dets_bit_packed(hn[:1024])
+        t0 = time.perf_counter()
+        dec.predict_obs_flips_from_dets_bit_packed(hn)
+        e2e_first_rate = per_call / (time.perf_counter() - t0)
         t0 = time.perf_counter()
         dec.predict_obs_flips_from_dets_bit_packed(hn)
         e2e_rate = per_call / (time.perf_counter() - t0)
@@ -92,7 +96,7 @@ def main():
         cpu_rate, cpu_s = bench.cpu_oracle_throughput(text, np.ascontiguousarray(hn[:n_cpu]), cores)
         row = {'config': name, 'detectors': int(dec.num_detectors), 'shots': calls * per_call, 'group_threads': int(group),
                'events_per_shot': events / (calls * per_call), 'gpu_shots_per_s': gpu_rate, 'gpu_us_per_shot': 1e6 / gpu_rate,
-               'host_api_shots_per_s': e2e_rate, 'cpu_oracle_shots_per_s': cpu_rate, 'cpu_cores': cores,
+               'host_api_shots_per_s': e2e_rate, 'host_api_first_call_shots_per_s': e2e_first_rate, 'cpu_oracle_shots_per_s': cpu_rate, 'cpu_cores': cores,
                'cpu_sample_shots': int(n_cpu), 'cpu_sample_s': cpu_s, 'gpu_over_cpu': gpu_rate / cpu_rate,
                'logical_error_rate': mistakes / (calls * per_call), 'oracle_checked_shots': int(len(first[0])),
                'weight_diffs': w_diff, 'prediction_diffs': p_diff, 'compile_s': compile_s, 'table_bytes': int(dec.table_bytes)}
