@@ -37,6 +37,26 @@ def test_product_does_not_link_the_oracle():
                 assert 'import oracle' not in text and 'oracle/' not in text.replace('the oracle', ''), f
 
 
+def test_decode_kernel_keeps_its_state_out_of_local_memory():
+    """The per-shot state (`Shot`, ~650 B of table views and arena pointers) lives in shared memory, one copy per warp.
+    A per-thread copy in local memory is what the kernel had until round 2 -- twice the global-load sectors of the whole
+    kernel -- and it comes back silently as soon as someone declares `Shot s;` in a kernel again. The cubin's resource
+    usage shows it: the stack frame grows by the size of the object."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    if not shutil.which('cuobjdump'):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run(['cuobjdump', '-res-usage', g.build_cuda()], capture_output=True, text=True).stdout
+    rows = re.findall(r'Function (\S*k_decodeILi(\d+)ELb0\S*):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)', out)
+    assert len(rows) >= 5, out[:500]
+    for name, group, reg, stack, shared in rows:
+        assert int(stack) <= 512, (group, stack)
+        assert int(shared) >= 2048, (group, shared)  # the warps' Shot objects (static shared memory)
+        if int(group) == 256:
+            assert int(reg) <= 80, reg  # three 256-thread groups per SM
+
+
 def test_compile_without_gpu_fails_loudly(cuda_lib):
     import chromobius_b200 as cb
     try:
