@@ -91,7 +91,10 @@ void cb200_free_string(char *s);
  *   weight_int_out  nullable; int64 per shot, the exact integer matching weight (parity hook)
  *   flags           CB200_IO_HOST or CB200_IO_DEVICE
  *   stats           nullable
- * A shot that cannot be decoded fails the whole call with CB200_ERR_DECODE, as the reference's exception does. */
+ * A shot that cannot be decoded fails the whole call with CB200_ERR_DECODE, as the reference's exception does.
+ * Large host batches (three chunks of 96 MB or more) are streamed: the decode kernel starts after the first chunk and a
+ * second stream delivers the rest while it runs. That needs launches and copies to overlap, so it is switched off when
+ * CUDA_LAUNCH_BLOCKING=1 or a profiler / sanitizer is injected into the process (or with CB200_NO_PIPELINE=1). */
 int cb200_decode_batch(cb200_decoder *dec, const uint8_t *dets, uint64_t num_shots, uint64_t row_stride, uint8_t *obs_out,
                        float *weight_out, int64_t *weight_int_out, uint32_t flags, cb200_batch_stats *stats);
 
