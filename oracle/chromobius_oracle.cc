@@ -1078,7 +1078,8 @@ struct DenseBlossom {
         // Start from per-vertex labels lab[u] = max_v w(u, v) (feasible: lab[u] + lab[v] >= 2 w(u, v)) and a greedy
         // matching on the edges that are tight under them (mutual best partners), lowest indices first. Any feasible
         // start with tight matched edges is a valid state of the primal-dual method; this one leaves only the
-        // vertices without a mutual best partner to the augmentation phases. (decode_core.h Blossom::solve does the same.)
+        // vertices without a mutual best partner to the second pass below and to the augmentation phases.
+        // (decode_core.h Blossom::solve does the same, step by step.)
         for (int u = 1; u <= n; ++u) {
             int64_t m = 0;
             for (int v = 1; v <= n; ++v) m = std::max(m, g[u][v].w);
@@ -1094,6 +1095,32 @@ struct DenseBlossom {
                     ++cnt;
                     break;
                 }
+        }
+        // Second pass: every vertex that is still free takes the lowest label its edges allow,
+        // lab[u] = max_v (2 w(u, v) - lab[v]) -- what the first dual steps of the phases would do one step at a time. The edge
+        // that defines it (lowest v on ties) is tight afterwards, and if its other end is free as well the pair is matched.
+        // Vertices are visited in ascending order and see the labels their predecessors were given.
+        for (int u = 1; u <= n; ++u) {
+            if (match[u] || lab[u] <= 0) continue;
+            bool any = false;
+            int64_t best = 0;
+            int bv = 0;
+            for (int v = 1; v <= n; ++v) {
+                if (v == u || g[u][v].w <= 0) continue;
+                int64_t t = 2 * g[u][v].w - lab[v];
+                if (!any || t > best) {
+                    any = true;
+                    best = t;
+                    bv = v;
+                }
+            }
+            if (!any) continue;
+            lab[u] = best;
+            if (!match[bv]) {
+                match[u] = bv;
+                match[bv] = u;
+                ++cnt;
+            }
         }
         while (matching()) ++cnt;
         return cnt;
