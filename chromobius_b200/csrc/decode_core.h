@@ -875,7 +875,7 @@ CB_HDN int ball_grow(const Shot &s, const G &g, BallTables &t, uint32_t src, int
     }
     t.nused = nused;
     t.nfront = nfront;
-#ifndef CB_TAIL_PROF
+#if !defined(CB_TAIL_PROF) && !defined(CB_SUBPROF)
     if (s.prof && lane == 0) {
         cb_atomic_add64((uint64_t *)&s.prof[19], prof_pops);
         cb_atomic_add64((uint64_t *)&s.prof[20], cb_clock() - prof_t0);
@@ -1000,7 +1000,7 @@ CB_HDN bool explore_event_near(Shot &s, const G &g, uint32_t i, int64_t radius, 
         s.nb_off[i] = (uint32_t)((off - 1) >> 4);
         s.nb_cnt[i] = nfound;
         s.R[i] = limit;
-#ifndef CB_TAIL_PROF
+#if !defined(CB_TAIL_PROF) && !defined(CB_SUBPROF)
         if (s.prof) cb_atomic_add64((uint64_t *)&s.prof[23], 1);
 #endif
     }
@@ -1124,6 +1124,10 @@ constexpr int BLOSSOM_PAR_MIN = CB_BLOSSOM_PAR_MIN;  // components with at least
 #define CB_BLOSSOM_PAR_MIN_FIXED 33  // > 32: the fixed 32-vertex layout never uses them
 #endif
 constexpr int BLOSSOM_PAR_MIN_FIXED = CB_BLOSSOM_PAR_MIN_FIXED;
+#ifndef CB_WARP_MIN_N
+#define CB_WARP_MIN_N 17
+#endif
+constexpr uint32_t WARP_SOLVER_MIN_N = CB_WARP_MIN_N;  // fixed-layout components from this size on: warp-synchronous solver
 
 template <class G, int CAP = 0>
 struct Blossom {
@@ -1261,6 +1265,15 @@ struct Blossom {
     // The run-time layout always has the warp helpers; of the fixed layouts only the 32-vertex one (and only from
     // BLOSSOM_PAR_MIN_FIXED events on): its O(n) loops are what a round waits for.
     static constexpr bool PAR_CLASS = CAP == 0 || (CAP == 32 && BLOSSOM_PAR_MIN_FIXED <= 32);
+    // -DCB_WARP_SOLVER: fixed-layout components of at least CB_WARP_MIN_N events are solved by the warp-synchronous
+    // solver (solve_w) on 32-lane warps. Off by default -- measured at d25 r100 (profiles/r02_kernel_experiments.txt):
+    // the 17..32-event class gets 25-33 % faster, the <= 8-event class 8 % slower, and the busier warps slow every
+    // other phase of the blocks sharing the SM by 4-6 %: 174.9 (all sizes) / 176.4 (>= 17) / 187.4 (>= 9) ms vs 171.1.
+#ifdef CB_WARP_SOLVER
+    static constexpr bool WARP_SOLVER = CAP > 0;
+#else
+    static constexpr bool WARP_SOLVER = false;
+#endif
     CB_HD bool is_par() const { return PAR_CLASS && par; }
     CB_HD int geu(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2] : ge()[(a * nxs() + b) * 2]; }
     CB_HD int gev(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2 + 1] : ge()[(a * nxs() + b) * 2 + 1]; }
@@ -1761,6 +1774,315 @@ struct Blossom {
                 if (st()[b] == b && S()[b] == 1 && lab()[b] == 0) expand_blossom(g, b);
         }
     }
+    // ---- warp-synchronous solver (fixed layouts) ------------------------------------------------------------------
+    // Every lane of the warp runs these functions with the same control flow. The O(n) loops of the method (slack
+    // search, dual step, label update, neighbour scan, row merges) are spread over the lanes -- vertex / node
+    // x = 1 + lane (+ 32) -- and reduced with warp primitives; the sequential bookkeeping (queue, flowers, augmenting)
+    // is done by lane 0 alone between two wsync()s. All solver state lives in shared memory, so after a wsync() every
+    // lane reads what lane 0 wrote; results lane 0 has to hand over travel through the command block. The steps and
+    // their order are those of the sequential solver above (lowest index first wherever it looks for "the first"), so
+    // matching and labels come out identical (tests/sim/warp_blossom_check.cc runs both side by side).
+    CB_HD void set_slack_w(const G &g, int x) {
+        const uint64_t best = g.min64(k_set_slack(g.lane(), g.lanes(), x));
+        if (g.lane() == 0) slack()[x] = best == ~uint64_t{0} ? 0 : (uint16_t)(best & 0xFFFF);
+        g.wsync();
+    }
+    CB_HDN void add_blossom_w(const G &g, int u, int lca, int v) {
+        in_shared();
+        if (g.lane() == 0) {
+            int b = n + 1;
+            CB_LOOP
+            while (b <= n_x && st()[b]) ++b;
+            if (b > n_x) ++n_x;
+            if (b >= NX) {
+                broken = true;
+            } else {
+                lab()[b] = 0;
+                S()[b] = 0;
+                match()[b] = match()[lca];
+                uint16_t *f = flower(b);
+                int len = 0;
+                f[len++] = (uint16_t)lca;
+                CB_LOOP
+                for (int x = u, y; x != lca && !broken; x = st()[pa()[y]]) {
+                    if (len + 2 > fls()) { broken = true; break; }
+                    f[len++] = (uint16_t)x;
+                    f[len++] = (uint16_t)(y = st()[match()[x]]);
+                    q_push(y);
+                }
+                reverse_tail(f, len);
+                CB_LOOP
+                for (int x = v, y; x != lca && !broken; x = st()[pa()[y]]) {
+                    if (len + 2 > fls()) { broken = true; break; }
+                    f[len++] = (uint16_t)x;
+                    f[len++] = (uint16_t)(y = st()[match()[x]]);
+                    q_push(y);
+                }
+                if (!broken) {
+                    fl_len()[b] = (uint16_t)len;
+                    set_st(b, b);
+                }
+            }
+            cmd()[4] = broken ? 0u : (uint32_t)b;
+        }
+        g.wsync();
+        const int b = (int)cmd()[4];
+        if (!b) return;
+        const int nx = n_x, len = fl_len()[b];
+        const uint16_t *f = flower(b);
+        // a lane owns the same x in the clearing pass and in every row merge: no barrier in between
+        k_blossom_clear(g.lane(), g.lanes(), b, nx);
+        CB_LOOP
+        for (int i = 0; i < len; ++i) k_merge_row(g.lane(), g.lanes(), b, f[i], nx);
+        g.wsync();
+        set_slack_w(g, b);
+    }
+    CB_HDN void expand_blossom_w(const G &g, int b) {
+        in_shared();
+        if (g.lane() == 0) {
+            uint16_t *f0 = flower(b);
+            const int len0 = fl_len()[b];
+            CB_LOOP
+            for (int i = 0; i < len0; ++i) set_st(f0[i], f0[i]);
+            const int xr0 = ffrom(b, geu(b, pa()[b]));
+            cmd()[4] = (uint32_t)xr0;
+            cmd()[5] = (uint32_t)get_pr(b, xr0);
+        }
+        g.wsync();
+        const int xr = (int)cmd()[4], pr = (int)cmd()[5];
+        const uint16_t *f = flower(b);
+        const int len = fl_len()[b];
+        CB_LOOP
+        for (int i = 0; i < pr; i += 2) {
+            const int xs = f[i], xns = f[i + 1];
+            if (g.lane() == 0) {
+                pa()[xs] = (uint16_t)geu(xns, xs);
+                S()[xs] = 1;
+                S()[xns] = 0;
+                slack()[xs] = 0;
+            }
+            g.wsync();
+            set_slack_w(g, xns);
+            if (g.lane() == 0) q_push(xns);
+        }
+        if (g.lane() == 0) {
+            S()[xr] = 1;
+            pa()[xr] = pa()[b];
+        }
+        CB_LOOP
+        for (int i = pr + 1; i < len; ++i) {
+            const int xs = f[i];
+            if (g.lane() == 0) S()[xs] = -1;
+            g.wsync();
+            set_slack_w(g, xs);
+        }
+        if (g.lane() == 0) st()[b] = 0;
+        g.wsync();
+    }
+    CB_HDN bool on_found_edge_w(const G &g, int eu, int ev) {
+        in_shared();
+        g.wsync();  // every lane is done with the state (and the command block) lane 0 is about to change
+        if (g.lane() == 0) {
+            const int u = st()[eu], v = st()[ev];
+            uint32_t code = 0;
+            if (S()[v] == -1) {
+                pa()[v] = (uint16_t)eu;
+                S()[v] = 1;
+                const int nu = st()[match()[v]];
+                slack()[v] = slack()[nu] = 0;
+                S()[nu] = 0;
+                q_push(nu);
+            } else if (S()[v] == 0) {
+                const int lca = get_lca(u, v);
+                if (!lca) {
+                    augment(u, v);
+                    augment(v, u);
+                    code = 1;
+                } else {
+                    code = 2;
+                    cmd()[1] = (uint32_t)u;
+                    cmd()[2] = (uint32_t)lca;
+                    cmd()[3] = (uint32_t)v;
+                }
+            }
+            cmd()[0] = code;
+        }
+        g.wsync();
+        const uint32_t code = cmd()[0];
+        if (code == 1) return true;
+        if (code == 2) add_blossom_w(g, (int)cmd()[1], (int)cmd()[2], (int)cmd()[3]);
+        return false;
+    }
+    CB_HDN bool matching_w(const G &g) {
+        in_shared();
+        const int lane = g.lane(), lanes = g.lanes();
+        const int64_t INF = INT64_MAX / 4;
+        k_phase_init(lane, lanes, n_x);
+        if (lane == 0) qh = qt = 0;
+        g.wsync();
+        // free top-level nodes become roots, ascending
+        CB_LOOP
+        for (int base = 1; base <= n_x; base += lanes) {
+            const int x = base + lane;
+            uint32_t hits = g.ballot(x <= n_x && st()[x] == x && !match()[x]);
+            if (lane == 0) {
+                CB_LOOP
+                while (hits) {
+                    const int r = base + (int)ctz32(hits);
+                    hits &= hits - 1;
+                    pa()[r] = 0;
+                    S()[r] = 0;
+                    q_push(r);
+                }
+            }
+        }
+        g.wsync();
+        if (qt == 0) return false;
+        int head = 0;  // queue head, the same in every lane (the member copy only serves q_put's overflow check)
+        CB_LOOP
+        for (;;) {
+            CB_LOOP
+            while (true) {
+                // (a wsync precedes every pass through here)
+                if (broken) return false;
+                if (head == qt) break;
+                const int u = q()[head];
+                head = head + 1 == qcs() ? 0 : head + 1;
+                if (S()[st()[u]] == 1) continue;
+                g.wsync();  // everyone has read the queue state before lane 0 changes it
+                if (lane == 0) qh = head;
+                // neighbours of u in ascending order: the lanes test 32 of them at a time; everything below the first
+                // tight edge only updates slacks (order-free), the tight edge itself is handled by the warp, and the
+                // rest is tested again afterwards -- handling an edge changes S / st / slack.
+                CB_LOOP
+                for (int k = 0; k < aws(); ++k) {
+                    uint32_t pending = adjm()[u * aws() + k];
+                    CB_LOOP
+                    while (pending) {
+                        const int v = 32 * k + lane;
+                        bool cand = false;
+                        int sv = 0;
+                        int64_t dist = 1;
+                        if ((pending >> lane) & 1u) {
+                            sv = st()[v];
+                            cand = st()[u] != sv;
+                            if (cand) dist = lab()[u] + lab()[v] - 2 * W()[u * ws() + v];
+                        }
+                        const uint32_t tight = g.ballot(cand && dist == 0);
+                        const uint32_t below = tight ? ((1u << ctz32(tight)) - 1u) : 0xFFFFFFFFu;
+                        if (cand && dist != 0 && ((below >> lane) & 1u)) update_slack(u, sv);
+                        g.wsync();
+                        if (!tight) break;
+                        const int fbit = (int)ctz32(tight);
+                        if (on_found_edge_w(g, u, 32 * k + fbit)) return true;
+                        pending &= ~(below | (1u << fbit));
+                    }
+                }
+            }
+            if (broken) return false;
+            const int64_t d = (int64_t)g.min64(k_dual_min(lane, lanes, n_x));
+            if (d >= INF) return false;
+            g.wsync();  // every lane has read the labels the minimum came from
+            k_lab_update(lane, lanes, n_x, d);
+            head = 0;
+            if (lane == 0) qh = qt = 0;
+            g.wsync();
+            CB_LOOP
+            for (int x0 = 1; x0 <= n_x;) {
+                int r = n_x + 1;
+                CB_LOOP
+                for (int base = x0; base <= n_x; base += lanes) {
+                    const int x = base + lane;
+                    const uint32_t hits = g.ballot(x <= n_x && tight_candidate(x));
+                    if (hits) {
+                        r = base + (int)ctz32(hits);
+                        break;
+                    }
+                }
+                if (r > n_x) break;
+                const int su = slack()[r];
+                if (on_found_edge_w(g, geu(su, r), gev(su, r))) return true;
+                x0 = r + 1;
+            }
+            CB_LOOP
+            for (int b = n + 1; b <= n_x; ++b)
+                if (st()[b] == b && S()[b] == 1 && lab()[b] == 0) expand_blossom_w(g, b);
+        }
+    }
+    // All lanes, after prepare(). Returns the number of matched pairs (the same value in every lane).
+    CB_HDN int solve_w(const G &g) {
+        in_shared();
+        const int lane = g.lane();
+        if (lane == 0) {
+            n_x = n;
+            vis_t = 0;
+        }
+        g.wsync();
+        int cnt = 0;
+        // greedy start, first pass (see solve()): the first free neighbour joined by a mutual-best edge
+        CB_LOOP
+        for (int u = 1; u <= n; ++u) {
+            if (match()[u] || lab()[u] <= 0) continue;
+            CB_LOOP
+            for (int k = 0; k < aws(); ++k) {
+                const int v = 32 * k + lane;
+                const bool ok = ((adjm()[u * aws() + k] >> lane) & 1u) && !match()[v] && W()[u * ws() + v] == lab()[u] && lab()[v] == lab()[u];
+                const uint32_t hits = g.ballot(ok);
+                if (hits) {
+                    if (lane == 0) {
+                        const int bv = 32 * k + (int)ctz32(hits);
+                        match()[u] = (uint16_t)bv;
+                        match()[bv] = (uint16_t)u;
+                    }
+                    ++cnt;
+                    break;
+                }
+            }
+            g.wsync();
+        }
+        // second pass: lowest feasible label, first maximum wins
+        CB_LOOP
+        for (int u = 1; u <= n; ++u) {
+            if (match()[u] || lab()[u] <= 0) continue;
+            bool any = false;
+            int64_t best = 0;
+            int bv = 0;
+            CB_LOOP
+            for (int k = 0; k < aws(); ++k) {
+                const int v = 32 * k + lane;
+                const bool ok = ((adjm()[u * aws() + k] >> lane) & 1u) && v != u;
+                const int64_t t = ok ? 2 * W()[u * ws() + v] - lab()[v] : INT64_MIN;
+                // maximum over the lanes (order-preserving map to unsigned), then the lowest lane that holds it
+                const uint64_t key = (uint64_t)t ^ (uint64_t{1} << 63);
+                const uint64_t kmax = ~g.min64(~key);
+                const uint32_t hits = g.ballot(ok && key == kmax);
+                if (hits) {
+                    const int64_t tm = (int64_t)(kmax ^ (uint64_t{1} << 63));
+                    if (!any || tm > best) {
+                        any = true;
+                        best = tm;
+                        bv = 32 * k + (int)ctz32(hits);
+                    }
+                }
+            }
+            if (!any) continue;
+            const bool free_end = !match()[bv];
+            g.wsync();  // every lane has read labels / partners before lane 0 changes them
+            if (lane == 0) {
+                lab()[u] = best;
+                if (free_end) {
+                    match()[u] = (uint16_t)bv;
+                    match()[bv] = (uint16_t)u;
+                }
+            }
+            if (free_end) ++cnt;
+            g.wsync();
+        }
+        CB_LOOP
+        while (matching_w(g)) ++cnt;
+        return cnt;
+    }
+
     // W must be filled (symmetric, 0 = absent). Master only. Returns the number of matched pairs; match()[1..n] = partners.
     // Every lane of the warp: per-vertex state, edge endpoints, adjacency rows and the starting labels (all O(n^2), data
     // parallel). W must be filled. Ends with the lanes synchronised.
@@ -1863,12 +2185,19 @@ CB_HD void uf_union(uint32_t *uf, uint32_t a, uint32_t b) {
 
 // Exact distance between two events of the same component, taken from whichever ball saw the other.
 CB_HD int64_t seen_distance(const Shot &s, uint32_t i, uint32_t j) {
-    const NbEntry *l = nb_list(s, i);
-    for (uint32_t k = 0; k < s.nb_cnt[i]; k++)
-        if (l[k].ev == j) return l[k].d;
-    l = nb_list(s, j);
-    for (uint32_t k = 0; k < s.nb_cnt[j]; k++)
-        if (l[k].ev == i) return l[k].d;
+    // both lists side by side (a pair seen from both sides carries the same distance in both)
+    const NbEntry *li = nb_list(s, i), *lj = nb_list(s, j);
+    const uint32_t ni = s.nb_cnt[i], nj = s.nb_cnt[j];
+    const uint32_t nmax = ni > nj ? ni : nj;
+    CB_LOOP
+    for (uint32_t k = 0; k < nmax; k++) {
+        uint32_t vi = NO_INDEX, vj = NO_INDEX;
+        int64_t xi = 0, xj = 0;
+        if (k < ni) { vi = li[k].ev; xi = li[k].d; }
+        if (k < nj) { vj = lj[k].ev; xj = lj[k].d; }
+        if (vi == j) return xi;
+        if (vj == i) return xj;
+    }
     return -1;
 }
 
@@ -1891,47 +2220,32 @@ CB_HDN bool solve_component_four(Shot &s, const uint32_t *mem) {
     const uint32_t e0 = mem[0], e1 = mem[1], e2 = mem[2], e3 = mem[3];
     int64_t d01 = -1, d02 = -1, d03 = -1, d12 = -1, d13 = -1, d23 = -1;
     {
-        const NbEntry *l = nb_list(s, e0);
-        const uint32_t n = s.nb_cnt[e0];
+        // the four lists side by side: one entry of each per step, so that their (independent) global loads overlap
+        const NbEntry *l0 = nb_list(s, e0), *l1 = nb_list(s, e1), *l2 = nb_list(s, e2), *l3 = nb_list(s, e3);
+        const uint32_t n0 = s.nb_cnt[e0], n1 = s.nb_cnt[e1], n2 = s.nb_cnt[e2], n3 = s.nb_cnt[e3];
+        uint32_t nmax = n0 > n1 ? n0 : n1;
+        if (n2 > nmax) nmax = n2;
+        if (n3 > nmax) nmax = n3;
         CB_LOOP
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t ev = l[k].ev;
-            if (ev == e1) d01 = l[k].d;
-            else if (ev == e2) d02 = l[k].d;
-            else if (ev == e3) d03 = l[k].d;
-        }
-    }
-    {
-        const NbEntry *l = nb_list(s, e1);
-        const uint32_t n = s.nb_cnt[e1];
-        CB_LOOP
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t ev = l[k].ev;
-            if (ev == e0) d01 = l[k].d;
-            else if (ev == e2) d12 = l[k].d;
-            else if (ev == e3) d13 = l[k].d;
-        }
-    }
-    {
-        const NbEntry *l = nb_list(s, e2);
-        const uint32_t n = s.nb_cnt[e2];
-        CB_LOOP
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t ev = l[k].ev;
-            if (ev == e0) d02 = l[k].d;
-            else if (ev == e1) d12 = l[k].d;
-            else if (ev == e3) d23 = l[k].d;
-        }
-    }
-    {
-        const NbEntry *l = nb_list(s, e3);
-        const uint32_t n = s.nb_cnt[e3];
-        CB_LOOP
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t ev = l[k].ev;
-            if (ev == e0) d03 = l[k].d;
-            else if (ev == e1) d13 = l[k].d;
-            else if (ev == e2) d23 = l[k].d;
+        for (uint32_t k = 0; k < nmax; k++) {
+            uint32_t v0 = NO_INDEX, v1 = NO_INDEX, v2 = NO_INDEX, v3 = NO_INDEX;
+            int64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+            if (k < n0) { v0 = l0[k].ev; x0 = l0[k].d; }
+            if (k < n1) { v1 = l1[k].ev; x1 = l1[k].d; }
+            if (k < n2) { v2 = l2[k].ev; x2 = l2[k].d; }
+            if (k < n3) { v3 = l3[k].ev; x3 = l3[k].d; }
+            if (v0 == e1) d01 = x0;
+            else if (v0 == e2) d02 = x0;
+            else if (v0 == e3) d03 = x0;
+            if (v1 == e0) d01 = x1;
+            else if (v1 == e2) d12 = x1;
+            else if (v1 == e3) d13 = x1;
+            if (v2 == e0) d02 = x2;
+            else if (v2 == e1) d12 = x2;
+            else if (v2 == e3) d23 = x2;
+            if (v3 == e0) d03 = x3;
+            else if (v3 == e1) d13 = x3;
+            else if (v3 == e2) d23 = x3;
         }
     }
     // pairings in fixed preference order: {01,23}, {02,13}, {03,12}; the first cheapest one wins
@@ -2080,8 +2394,13 @@ CB_HD uint64_t blossom_bytes(uint32_t n) {
 }
 
 // Set-up shared by every solver class, all lanes: clears the weight matrix W (row stride ws) and fills it from the
-// members' neighbour lists (global memory, one member per lane). Only pairs inside the component take part; pairs seen
-// across components are guarded by the dual check. Returns `big` (weights are big - distance).
+// members' neighbour lists (global memory). Only pairs inside the component take part; pairs seen across components are
+// guarded by the dual check. Weights are BLOSSOM_BIG - distance: the solver only ever looks at label sums minus doubled
+// weights, so its run does not depend on the constant (the oracle uses max distance + 2 and takes the same steps) --
+// a fixed one saves the extra pass over the lists that a data-dependent one needs. Distances are < 2^49 (node ids have
+// 24 bits, edge weights 25). The lists are walked by lanes / n lanes per member (n < lanes), each entry by one lane: the
+// walk is a chain of three dependent global loads per entry, so its length is what the set-up costs.
+constexpr int64_t BLOSSOM_BIG = int64_t{1} << 52;
 template <class G>
 CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n, const uint32_t *mem, int64_t *W, uint32_t ws) {
     const uint32_t lane = (uint32_t)g.lane(), lanes = (uint32_t)g.lanes();
@@ -2090,30 +2409,25 @@ CB_HDN int64_t blossom_fill_weights(Shot &s, const G &g, uint32_t r, uint32_t n,
     CB_LOOP
     for (uint32_t a = lane; a < n; a += lanes) s.lidx[mem[a]] = a + 1;
     g.wsync();
-    int64_t big = 2;
+    const uint32_t per = n < lanes ? lanes / n : 1u;  // lanes per member
+    const uint32_t sweep = lanes / per;               // members per sweep
+    const uint32_t sub = lane % per;
     CB_LOOP
-    for (uint32_t a = lane; a < n; a += lanes) {
+    for (uint32_t a = lane / per; a < n; a += sweep) {
         const NbEntry *l = nb_list(s, mem[a]);
         const uint32_t cnt = s.nb_cnt[mem[a]];
         CB_LOOP
-        for (uint32_t k = 0; k < cnt; k++)
-            if (s.root[l[k].ev] == r && l[k].d + 2 > big) big = l[k].d + 2;
-    }
-    big = (int64_t)(~g.min64(~(uint64_t)big));  // maximum over the lanes
-    CB_LOOP
-    for (uint32_t a = lane; a < n; a += lanes) {
-        const NbEntry *l = nb_list(s, mem[a]);
-        const uint32_t cnt = s.nb_cnt[mem[a]];
-        CB_LOOP
-        for (uint32_t k = 0; k < cnt; k++) {
-            if (s.root[l[k].ev] != r) continue;
-            const uint32_t b = s.lidx[l[k].ev];
-            W[(a + 1) * ws + b] = big - l[k].d;  // a pair seen from both sides writes the same value twice
-            W[b * ws + (a + 1)] = big - l[k].d;
+        for (uint32_t k = sub; k < cnt; k += per) {
+            const uint32_t ev = l[k].ev;
+            if (s.root[ev] != r) continue;
+            const uint32_t b = s.lidx[ev];
+            const int64_t w = BLOSSOM_BIG - l[k].d;
+            W[(a + 1) * ws + b] = w;  // a pair seen from both sides writes the same value twice
+            W[b * ws + (a + 1)] = w;
         }
     }
     g.wsync();
-    return big;
+    return BLOSSOM_BIG;
 }
 
 // Write-back shared by every solver class, all lanes, one member each.
@@ -2166,11 +2480,52 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     g.wsync();
     const unsigned long long prof_t0 = s.prof ? cb_clock() : 0;
     const int64_t big = blossom_fill_weights(s, g, r, n, mem, bl.W(), (uint32_t)bl.ws());
+#ifdef CB_SUBPROF  // diagnostic build: set-up / prepare / solve / write-back cycles of one size class in slots 16..19
+    const bool subprof = s.prof && g.lane() == 0 && (n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3))) == CB_SUBPROF;
+    unsigned long long sub_t = cb_clock();
+    if (subprof) {
+        cb_atomic_add64((uint64_t *)&s.prof[16], sub_t - prof_t0);
+        cb_atomic_add64((uint64_t *)&s.prof[22], n);
+        cb_atomic_add64((uint64_t *)&s.prof[23], 1);
+    }
+#endif
     bl.prepare(g);
+#ifdef CB_SUBPROF
+    if (subprof) {
+        unsigned long long now_ = cb_clock();
+        cb_atomic_add64((uint64_t *)&s.prof[17], now_ - sub_t);
+        sub_t = now_;
+    }
+#endif
     uint32_t pairs = 0;
-    if (g.lane() == 0) {
+    if (BL::WARP_SOLVER && g.lanes() == 32 && n >= WARP_SOLVER_MIN_N) {
+        // fixed layouts on a 32-lane warp: every lane runs the warp-synchronous solver
+        pairs = (uint32_t)bl.solve_w(g);
+        if (g.lane() == 0 && s.prof) {
+            int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
+            cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
+#ifndef CB_XPROF2
+            cb_atomic_add64((uint64_t *)&s.prof[12 + bucket], 1);
+#endif
+#ifdef CB_SUBPROF
+            if (subprof) {
+                unsigned long long now_ = cb_clock();
+                cb_atomic_add64((uint64_t *)&s.prof[18], now_ - sub_t);
+                sub_t = now_;
+            }
+#endif
+        }
+        if (bl.broken) pairs = NO_INDEX;
+    } else if (g.lane() == 0) {
         pairs = (uint32_t)bl.solve(g);
         bl.release_workers(g);
+#ifdef CB_SUBPROF
+        if (subprof) {
+            unsigned long long now_ = cb_clock();
+            cb_atomic_add64((uint64_t *)&s.prof[18], now_ - sub_t);
+            sub_t = now_;
+        }
+#endif
         if (s.prof) {
             int bucket = n <= 8 ? 0 : (n <= 16 ? 1 : (n <= 32 ? 2 : 3));
             cb_atomic_add64((uint64_t *)&s.prof[8 + bucket], cb_clock() - prof_t0);
@@ -2189,6 +2544,9 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
         return;
     }
     blossom_write_back(s, g, n, mem, pairs, big, bl.match(), bl.lab());
+#ifdef CB_SUBPROF
+    if (subprof) cb_atomic_add64((uint64_t *)&s.prof[19], cb_clock() - sub_t);
+#endif
 }
 
 // Exact solve of component c by the dense blossom; every lane of the warp calls this together. Lane 0 drives the solver,
@@ -3326,7 +3684,9 @@ CB_HD void decode_shot(Shot &s, const DecodeParams &p, uint32_t shot, const G &g
             pt.t[3] = pt.t[8] + pt.t[9] + pt.t[10];
             for (int k = 0; k < 7; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[k], pt.t[k]);
             cb_atomic_add64((uint64_t *)&p.phase_cycles[7], 1);
+#ifndef CB_SUBPROF
             for (int k = 8; k < 11; k++) cb_atomic_add64((uint64_t *)&p.phase_cycles[8 + k], pt.t[k]);
+#endif
 #if defined(CB_TAIL_PROF) && defined(__CUDA_ARCH__)
             // diagnostic build: slot 19 = longest shot (cycles), slot 23 = shots longer than 8 M cycles (~4 ms)
             unsigned long long tot_ = 0;
