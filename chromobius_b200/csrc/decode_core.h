@@ -1269,11 +1269,20 @@ struct Blossom {
     // solver (solve_w) on 32-lane warps. Off by default -- measured at d25 r100 (profiles/r02_kernel_experiments.txt):
     // the 17..32-event class gets 25-33 % faster, the <= 8-event class 8 % slower, and the busier warps slow every
     // other phase of the blocks sharing the SM by 4-6 %: 174.9 (all sizes) / 176.4 (>= 17) / 187.4 (>= 9) ms vs 171.1.
+    // The run-time layout (components of more than 32 events, 0.2 per shot but ~1 M cycles each on one lane) always uses
+    // it unless -DCB_NO_WARP_SOLVER_BIG: there the neighbour scan is what the time goes into, and nothing else of the
+    // block runs meanwhile.
 #ifdef CB_WARP_SOLVER
-    static constexpr bool WARP_SOLVER = CAP > 0;
+    static constexpr bool WARP_SOLVER_FIXED = true;
 #else
-    static constexpr bool WARP_SOLVER = false;
+    static constexpr bool WARP_SOLVER_FIXED = false;
 #endif
+#ifdef CB_NO_WARP_SOLVER_BIG
+    static constexpr bool WARP_SOLVER_BIG = false;
+#else
+    static constexpr bool WARP_SOLVER_BIG = true;
+#endif
+    static constexpr bool WARP_SOLVER = CAP > 0 ? WARP_SOLVER_FIXED : WARP_SOLVER_BIG;
     CB_HD bool is_par() const { return PAR_CLASS && par; }
     CB_HD int geu(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2] : ge()[(a * nxs() + b) * 2]; }
     CB_HD int gev(int a, int b) const { return is_wide() ? ((const uint16_t *)ge())[(a * nxs() + b) * 2 + 1] : ge()[(a * nxs() + b) * 2 + 1]; }
@@ -2498,7 +2507,7 @@ CB_HDN void solve_component_blossom_t(Shot &s, const G &g, uint32_t c, uint8_t *
     }
 #endif
     uint32_t pairs = 0;
-    if (BL::WARP_SOLVER && g.lanes() == 32 && n >= WARP_SOLVER_MIN_N) {
+    if (BL::WARP_SOLVER && g.lanes() == 32 && (CAP == 0 || n >= WARP_SOLVER_MIN_N)) {
         // fixed layouts on a 32-lane warp: every lane runs the warp-synchronous solver
         pairs = (uint32_t)bl.solve_w(g);
         if (g.lane() == 0 && s.prof) {

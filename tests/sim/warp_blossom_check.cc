@@ -121,12 +121,14 @@ static int run_case(int n, const std::vector<int64_t> &w, int id) {
 int main(int argc, char **argv) {
     int cases = argc > 1 ? atoi(argv[1]) : 300;
     uint64_t seed = argc > 2 ? strtoull(argv[2], nullptr, 10) : 1;
+    const int big_n = argc > 3 ? atoi(argv[3]) : 90;
     std::mt19937_64 rng(seed);
     int failures = 0;
     const int64_t BIG = int64_t{1} << 52;
     for (int id = 0; id < cases; id++) {
-        const int cap = (id & 1) ? 32 : 16;
-        int n = 2 + (int)(rng() % (cap - 1));  // 2 .. cap
+        // fixed layouts of 16 / 32 vertices, and the run-time layout (CAP 0) with up to `big_n` vertices
+        const int cap = (id % 3 == 2) ? 0 : ((id & 1) ? 32 : 16);
+        int n = cap ? 2 + (int)(rng() % (cap - 1)) : 33 + (int)(rng() % (big_n - 32));
         int style = (int)(rng() % 4);
         // points on a line / small integer distances produce many ties and blossoms; odd n and sparse graphs included
         std::vector<int64_t> w((n + 1) * (n + 1), 0);
@@ -139,7 +141,7 @@ int main(int argc, char **argv) {
                 int64_t d = style == 1 ? 2 * (int64_t)(1 + rng() % 5) : 2 * (1 + llabs(pos[u] - pos[v]) + (int64_t)(rng() % 3));
                 w[u * (n + 1) + v] = w[v * (n + 1) + u] = BIG - d;
             }
-        failures += cap == 16 ? run_case<16>(n, w, id) : run_case<32>(n, w, id);
+        failures += cap == 16 ? run_case<16>(n, w, id) : (cap == 32 ? run_case<32>(n, w, id) : run_case<0>(n, w, id));
     }
     printf("%d cases (%d formed blossoms, %d without a perfect matching), %d failures\n", cases, g_blossom_cases, g_imperfect, failures);
     return failures ? 1 : 0;

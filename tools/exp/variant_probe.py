@@ -24,6 +24,8 @@ for rep in range(3):
 st = dec.last_stats
 print('%s %s: decode %.2f ms (%.0f shots/s) rounds/shot %.2f retried %d wsum %d' % (
     label, name[:24], best, shots / (best * 1e-3), st.matcher_rounds / shots, st.num_retried_shots, int(wint.sum())), flush=True)
+if os.environ.get('PROBE_SAVE'):
+    np.savez(os.environ['PROBE_SAVE'], pred=pred, wint=wint)
 if check:
     import oracle
     m = np.zeros(shots, np.uint64)
