@@ -57,6 +57,24 @@ def test_decode_kernel_keeps_its_state_out_of_local_memory():
             assert int(reg) <= 80, reg  # three 256-thread groups per SM
 
 
+def test_decode_kernel_solver_classes_are_the_measured_configuration():
+    """Which blossom solver each size class runs is a measured choice: the run-time layout of components
+    over 32 events is solved by the whole warp (solve_w; the master / worker command dispatch is gone from the device code),
+    the fixed 16- and 32-vertex layouts by the sequential solver. The cubin's symbols show what was compiled in."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    if not shutil.which('cuobjdump') or not shutil.which('c++filt'):
+        pytest.skip('cuobjdump / c++filt not available')
+    elf = subprocess.run(['cuobjdump', '-elf', g.build_cuda()], capture_output=True, text=True).stdout
+    mangled = sorted(set(re.findall(r'_ZN5cb2007Blossom\w+', elf)))
+    names = subprocess.run(['c++filt'], input='\n'.join(mangled), capture_output=True, text=True).stdout
+    assert re.search(r'Blossom<.*DevGroup<256>, 0>::solve_w', names), names[:2000]
+    assert 'worker_loop' not in names and '::dispatch(' not in names
+    assert not re.search(r'Blossom<.*DevGroup<256>, (16|32)>::solve_w', names)
+    assert re.search(r'Blossom<.*DevGroup<256>, 16>::matching', names) and re.search(r'Blossom<.*DevGroup<256>, 32>::matching', names)
+
+
 def test_compile_without_gpu_fails_loudly(cuda_lib):
     import chromobius_b200 as cb
     try:
